@@ -1,0 +1,103 @@
+/* mps_b200.h -- C ABI of the B200-native matrix-product-state gate engine (libmps_b200.so).
+ *
+ * This is the drop-in boundary for the tensor back end of TNQVM's `exatn-mps` visitor
+ * (reference: tnqvm/visitors/exatn-mps/ExaTnMpsVisitor.{hpp,cpp}).  Every entry point below
+ * names the reference call site it replaces.  Plain pointers and sizes only; complex128 is an
+ * interleaved double[2]; all tensors are column-major, site index order (left bond, physical,
+ * right bond) exactly as the reference keeps them inside ExaTN (ExaTnMpsVisitor.cpp:1684-1695).
+ *
+ * Conventions (SURVEY.md section 8a cheat-sheet, verified against the reference's gtests):
+ *   - qubit 0 is the least-significant bit of a state-vector index (ExaTnMpsVisitor.cpp:1674-1682)
+ *   - 1q gate: new[b] = sum_i m[b][i] old[i], m row-major as in tnqvm/base/Gates.hpp
+ *   - 2q gate: m row-major 4x4, index = 2*bit(q0)+bit(q1) whichever of q0,q1 is the left site
+ *     (ExaTnMpsVisitor.cpp:1492-1499); |q0-q1| must be 1 (assert at :1398)
+ *   - "exp-val-z" and sampling use the raw, un-normalised state (ExaTnMpsVisitor.cpp:616-644)
+ *
+ * Error model: every function returns 0 on success, non-zero on failure; mps_last_error() gives
+ * the message.  No C++ exception crosses this boundary.  A handle is confined to one host thread;
+ * work is asynchronous on the handle's CUDA stream until a read-back or mps_sync().
+ * There is no CPU fallback: mps_create fails when no CUDA device is usable.
+ */
+#ifndef MPS_B200_H_
+#define MPS_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mps_b200_handle* mps_handle_t;
+
+/* gauge of the SVD write-back */
+#define MPS_GAUGE_REFERENCE 0 /* Q_lo = U sqrt(S), Q_hi = sqrt(S) V^H : ExaTN SVDLR, ExaTnMpsVisitor.cpp:1623 */
+#define MPS_GAUGE_LEFT 1      /* Q_lo = U,        Q_hi = S V^H  (orthogonality centre moves right)           */
+#define MPS_GAUGE_RIGHT 2     /* Q_lo = U S,      Q_hi = V^H    (orthogonality centre moves left)            */
+
+/* ExatnMpsVisitor::initialize (ExaTnMpsVisitor.cpp:173-346): |0...0> with all bonds 1.
+ * max_bond <= 0 -> no limit ("max-bond-dim", :265-271); svd_cutoff < 0 -> DBL_MIN ("svd-cutoff", :257-263).
+ * n_registers > 1 builds that many independent n_qubits-wide registers in one handle (qubit index
+ * = register*n_qubits + q); independent circuits then share batched kernel launches (config 4). */
+int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, int gauge, int device,
+               uint64_t seed, mps_handle_t* out);
+int mps_destroy(mps_handle_t h);
+const char* mps_last_error(mps_handle_t h); /* h may be NULL: last mps_create error */
+int mps_reset(mps_handle_t h);              /* back to |0...0>, ExaTnMpsVisitor.cpp:273-326 */
+
+/* keys: "cutoff_on_sqrt" (computePartialNormsSync ambiguity), "fuse_1q", "renormalize",
+ * "jacobi_tol", "jacobi_max_sweeps", "profile", "layer_batch" (0 = execute gate by gate) */
+int mps_set_option(mps_handle_t h, const char* key, double value);
+
+/* applyGate 1q branch, ExaTnMpsVisitor.cpp:1185-1292.  m = row-major 2x2 complex. */
+int mps_apply_1q(mps_handle_t h, int q, const double m[8]);
+/* applyTwoQubitGate, ExaTnMpsVisitor.cpp:1387-1731 + truncateSvdTensors :2366-2536. m = row-major 4x4. */
+int mps_apply_2q(mps_handle_t h, int q0, int q1, const double m[32]);
+/* count independent (or not: dependencies are resolved) 2q gates in one call */
+int mps_apply_layer(mps_handle_t h, int count, const int* q0, const int* q1, const double* mats);
+/* gates are queued and executed in dependency layers; flush forces execution, sync also waits */
+int mps_flush(mps_handle_t h);
+int mps_sync(mps_handle_t h);
+
+/* "norm" extra-info, ExaTnMpsVisitor.cpp:604-612 (<psi|psi>, by transfer-matrix sweep) */
+int mps_norm(mps_handle_t h, int reg, double* out);
+/* "exp-val-z", ExaTnMpsVisitor.cpp:616-644: <psi| prod Z_q |psi>, NOT divided by the norm */
+int mps_expval_z(mps_handle_t h, int reg, int nq, const int* qubits, double* out);
+/* <Z_k> for every qubit of a register (left/right environment sweeps; ITensorMPSVisitor.cpp:173-250) */
+int mps_expval_z_all(mps_handle_t h, int reg, double* out_n);
+/* <Z_i Z_j> for a list of pairs */
+int mps_expval_zz_pairs(mps_handle_t h, int reg, int npairs, const int* qi, const int* qj, double* out);
+/* computeWaveFuncSlice, ExaTnMpsVisitor.cpp:2588-2675: bits[k] in {0,1} fixed or -1 = open leg.
+ * out receives 2^(#open) complex amplitudes (open qubits ordered by index, lowest = fastest). */
+int mps_amplitude(mps_handle_t h, int reg, const int8_t* bits, double* out, size_t* len);
+/* full state vector, evaluateSync(ket) at ExaTnMpsVisitor.cpp:591-597 (n_qubits <= 30) */
+int mps_statevector(mps_handle_t h, int reg, double* out);
+
+/* visit(Measure), ExaTnMpsVisitor.cpp:991-994: records the qubit; character i of a sample string
+ * belongs to the i-th recorded qubit */
+int mps_measure(mps_handle_t h, int q);
+int mps_clear_measure(mps_handle_t h);
+int mps_seed(mps_handle_t h, uint64_t seed); /* {"seed", int}, TNQVM.hpp:114-117 */
+/* finalize() sampling: n < 20 -> GenerateSamples on the state vector (GateMatrixAlgebra.hpp:125-156),
+ * n >= 20 -> per-shot sequential RDM sampling (getMeasureSample, ExaTnMpsVisitor.cpp:2211-2364).
+ * out: shots * n_measured chars (no terminators); n_out = strings actually produced. */
+int mps_sample(mps_handle_t h, int reg, int shots, char* out, int* n_out);
+
+int mps_bond_dims(mps_handle_t h, int* out);                                           /* n_total-1 entries */
+int mps_singular_values(mps_handle_t h, int bond, double* out, int cap, int* count);   /* of the last SVD on that bond */
+int mps_discarded_weight(mps_handle_t h, double* out); /* sum over truncations of discarded/total weight */
+int mps_get_site(mps_handle_t h, int k, double* out, int shape[3]);                    /* out may be NULL (shape only) */
+int mps_set_site(mps_handle_t h, int k, const double* in, int dl, int dr);
+
+/* site-sharded multi-GPU support (replaces replicateTensorSync at ExaTnMpsVisitor.cpp:2088-2158):
+ * device pointer of a site tensor for NCCL send/recv, and adoption of a received tensor */
+int mps_site_device_ptr(mps_handle_t h, int k, void** dptr, int shape[3]);
+int mps_resize_site(mps_handle_t h, int k, int dl, int dr, void** dptr);
+
+/* counters: [0] 2q gates executed, [1] 1q kernel gates, [2] layers, [3] jacobi sweeps, [4] kernel launches,
+ * [5] ms merge GEMM, [6] ms SVD, [7] ms truncate+write-back (5..7 only with option "profile") */
+int mps_stats(mps_handle_t h, double* out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,90 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/mps_b200.h declares (no compute
+without a GPU), the product refuses to run without CUDA (no fallback), and the host-side circuit logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import tnqvm_b200
+from tnqvm_b200 import abi, circuits as Cc, gates
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "mps_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mps_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) >= 25
+    L = ctypes.CDLL(abi.lib_path())
+    for s in syms:
+        assert hasattr(L, s), "libmps_b200.so does not export %s" % s
+    assert set(syms) == set(abi.SYMBOLS), set(syms) ^ set(abi.SYMBOLS)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(abi.MpsError, match="no CUDA device|CUDA"):
+        tnqvm_b200.B200MPS(4)
+
+
+def test_product_does_not_import_oracle():
+    import subprocess, sys
+    code = "import sys; sys.path.insert(0, %r); import tnqvm_b200; assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported'" % ROOT
+    subprocess.check_call([sys.executable, "-c", code])
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tnqvm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, os.path.join(dirpath, f)
+
+
+def test_gate_matrices_unitary_and_conventions():
+    for nm, pr in [("H", ()), ("Rx", (0.3,)), ("U", (0.1, 0.2, 0.3)), ("CNOT", ()), ("fSim", (0.4, 0.6)), ("iSwap", ()), ("CPhase", (0.7,))]:
+        m = gates.gate_matrix(nm, pr)
+        assert np.allclose(m @ m.conj().T, np.eye(m.shape[0]), atol=1e-14)
+    assert gates.gate_matrix("CNOT")[3, 2] == 1 and gates.gate_matrix("fSim", (0.0, 0.5))[3, 3] == np.exp(-0.5j)
+    assert np.array_equal(gates.gate_matrix("Bogus"), np.eye(2))   # ExatnUtils.cpp:112
+
+
+def test_xasm_roundtrip_and_counts():
+    c = Cc.brickwork(6, 3, seed=1, prefix_ghz=True) + [("fSim", (1, 2), (0.25, -0.5)), ("Measure", (3,), ())]
+    n, c2 = Cc.load_xasm(Cc.to_xasm(c))
+    assert n == 6 and len(c2) == len(c)
+    for a, b in zip(c, c2):
+        assert a[0] == b[0] and tuple(a[1]) == tuple(b[1]) and np.allclose(a[2], b[2])
+
+
+def test_nearest_neighbor_matches_reference_swap_bookkeeping():
+    # NearestNeighborTransformTester.cpp: all 2q distances become 1; CNOT(0,3) -> swaps (0,1) then (3,2)... back again
+    out = Cc.nearest_neighbor([("CNOT", (0, 3), ())])
+    assert all(abs(g[1][0] - g[1][1]) == 1 for g in out if len(g[1]) == 2)
+    assert [g[0] for g in out] == ["Swap", "Swap", "CNOT", "Swap", "Swap"]
+    assert out[0][1] == (0, 1) and out[1][1] == (3, 2) and out[2][1] == (1, 2)
+    out = Cc.nearest_neighbor([("CNOT", (3, 1), ())], max_distance=2)
+    assert out == [("CNOT", (3, 1), ())]
+    # swap count: distance d needs 2*(d-1) swaps
+    for d in range(2, 9):
+        o = Cc.nearest_neighbor([("CZ", (0, d), ())])
+        assert sum(1 for g in o if g[0] == "Swap") == 2 * (d - 1)
+
+
+def test_config_generators_shapes():
+    c2 = Cc.brickwork(50, 20, seed=12345)
+    assert Cc.count_gates(c2) == (1000, 490)
+    q = Cc.nearest_neighbor(Cc.qaoa_ring(100, 4))
+    assert all(abs(g[1][0] - g[1][1]) == 1 for g in q if len(g[1]) == 2)
+    assert Cc.count_gates(Cc.hea(64, 4, seed=0)) == (512, 252)
+    syc = "/root/reference/examples/sycamore/resources/sycamore_53_14_0.xasm"
+    if os.path.exists(syc):
+        n, c = Cc.load_xasm(open(syc).read())
+        assert n == 53 and Cc.count_gates(c) == (2527, 301)
+        assert Cc.count_gates(Cc.nearest_neighbor(c))[1] == 1897

@@ -1,0 +1,973 @@
+// Host engine of the B200 MPS gate-application path + the C ABI of include/mps_b200.h.
+//
+// What the reference does per gate through ~12 ExaTN tensor create/destroy calls, two string-parsed
+// network rebuilds, three host copies of theta and >= 10 global syncs (ExaTnMpsVisitor.cpp:1387-1731),
+// this engine does as: queue the gate -> group queued gates into dependency layers (gates of a layer
+// touch disjoint sites) -> per layer four batched launches families on one stream:
+//   theta GEMM+gate (DMMA)  ->  block-Jacobi sweeps  ->  sort/truncate  ->  gather + back-multiply GEMM.
+// The only host synchronisation per layer is the read-back of the kept bond dimensions.
+#include <algorithm>
+#include <array>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+#include <cstdlib>
+
+#include "../../include/mps_b200.h"
+#include "kernels.h"
+
+using namespace mpsb200;
+typedef std::complex<double> cplx;
+
+#define CK(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e__ = (call);                                                                                 \
+    if (e__ != cudaSuccess)                                                                                   \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + \
+                               std::to_string(__LINE__));                                                     \
+  } while (0)
+
+namespace {
+
+struct SiteBuf {
+  double2* d = nullptr;
+  size_t cap = 0;   // complex elements
+  int dl = 1, dr = 1;
+};
+
+struct QGate {
+  int q0, q1;       // q1 < 0: single-qubit gate
+  cplx m[16];
+};
+
+// bump allocator over one grow-only device buffer
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  void reset() { off = 0; }
+  size_t reserve(size_t bytes) {   // returns offset
+    size_t o = (off + 255) & ~size_t(255);
+    off = o + bytes;
+    return o;
+  }
+};
+
+static std::string g_create_error;
+
+// developer aid: MPS_B200_BACKTRACE=1 prints a native backtrace on SIGSEGV
+static void segv_handler(int sig) {
+  void* frames[64];
+  int n = backtrace(frames, 64);
+  backtrace_symbols_fd(frames, n, 2);
+  _exit(128 + sig);
+}
+
+}  // namespace
+
+struct mps_b200_handle {
+  int nq = 0, nreg = 1, ntot = 0;
+  int max_bond = INT_MAX - 1;
+  double cutoff = DBL_MIN;
+  int gauge = 0, device = 0;
+  int cutoff_on_sqrt = 0, fuse_1q = 1, renorm = 0, profile = 0, layer_batch = 1;
+  double jacobi_tol = 0.0;   // 0 -> sqrt(M) * eps
+  double null_tol = 0.0;     // 0 -> 10 * jacobi tolerance
+  int max_sweeps = 40;
+  cudaStream_t stream = nullptr;
+  std::vector<SiteBuf> sites;
+  std::vector<char> has1q;
+  std::vector<std::array<cplx, 4>> p1q;
+  std::vector<QGate> queue;
+  std::vector<std::vector<double>> sv;   // per bond
+  std::vector<int> measure;
+  std::mt19937_64 rng;
+  double discarded = 0.0;
+  std::string err;
+  // device workspace
+  Arena ws;
+  // pinned staging: two regions (pre-sync / post-sync uploads), plus read-back area
+  char* pin[2] = {nullptr, nullptr};
+  size_t pin_cap[2] = {0, 0};
+  char* pin_rb = nullptr;
+  size_t pin_rb_cap = 0;
+  cudaEvent_t ev[6] = {};
+  // counters
+  double n2q = 0, n1q = 0, nlayers = 0, nsweeps = 0, nlaunch = 0, ms_theta = 0, ms_svd = 0, ms_wb = 0;
+
+  // ------------------------------------------------------------------ memory helpers
+  void ensure_ws(size_t bytes) {
+    if (bytes <= ws.cap) return;
+    CK(cudaStreamSynchronize(stream));
+    if (ws.base) CK(cudaFree(ws.base));
+    size_t ncap = std::max(bytes + bytes / 4, size_t(1) << 22);
+    CK(cudaMalloc(&ws.base, ncap));
+    ws.cap = ncap;
+  }
+  char* pinned(int which, size_t bytes) {
+    if (bytes > pin_cap[which]) {
+      CK(cudaStreamSynchronize(stream));
+      if (pin[which]) CK(cudaFreeHost(pin[which]));
+      size_t ncap = std::max(bytes * 2, size_t(1) << 16);
+      CK(cudaMallocHost(&pin[which], ncap));
+      pin_cap[which] = ncap;
+    }
+    return pin[which];
+  }
+  char* pinned_rb(size_t bytes) {
+    if (bytes > pin_rb_cap) {
+      CK(cudaStreamSynchronize(stream));
+      if (pin_rb) CK(cudaFreeHost(pin_rb));
+      size_t ncap = std::max(bytes * 2, size_t(1) << 16);
+      CK(cudaMallocHost(&pin_rb, ncap));
+      pin_rb_cap = ncap;
+    }
+    return pin_rb;
+  }
+  void ensure_site(int k, int dl, int dr, bool keep_data) {
+    SiteBuf& s = sites[k];
+    size_t need = (size_t)2 * dl * dr;
+    if (need > s.cap) {
+      size_t ncap = need;
+      // grow geometrically but never beyond what max_bond allows
+      if (max_bond < (1 << 20)) ncap = std::max(need, std::min((size_t)2 * max_bond * max_bond, need * 2));
+      double2* nd = nullptr;
+      CK(cudaMalloc(&nd, ncap * sizeof(double2)));
+      if (s.d) {
+        if (keep_data)
+          CK(cudaMemcpyAsync(nd, s.d, (size_t)2 * s.dl * s.dr * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaFree(s.d));
+      }
+      s.d = nd;
+      s.cap = ncap;
+    }
+    s.dl = dl;
+    s.dr = dr;
+  }
+
+  // ------------------------------------------------------------------ state
+  void reset_state() {
+    CK(cudaStreamSynchronize(stream));
+    queue.clear();
+    std::fill(has1q.begin(), has1q.end(), 0);
+    measure.clear();
+    discarded = 0.0;
+    const cplx zero_state[2] = {cplx(1, 0), cplx(0, 0)};
+    for (int k = 0; k < ntot; ++k) {
+      ensure_site(k, 1, 1, false);
+      CK(cudaMemcpyAsync(sites[k].d, zero_state, sizeof(zero_state), cudaMemcpyHostToDevice, stream));
+    }
+    CK(cudaStreamSynchronize(stream));
+    for (auto& v : sv) v.assign(1, 1.0);
+  }
+
+  int reg_of(int q) const { return q / nq; }
+
+  // ------------------------------------------------------------------ gate queue
+  void push_1q(int q, const cplx* m) {
+    if (q < 0 || q >= ntot) throw std::runtime_error("qubit index out of range");
+    if (fuse_1q) {
+      if (!has1q[q]) {
+        has1q[q] = 1;
+        p1q[q] = {m[0], m[1], m[2], m[3]};
+      } else {   // new = m * old
+        auto o = p1q[q];
+        p1q[q] = {m[0] * o[0] + m[1] * o[2], m[0] * o[1] + m[1] * o[3], m[2] * o[0] + m[3] * o[2], m[2] * o[1] + m[3] * o[3]};
+      }
+    } else {
+      QGate g;
+      g.q0 = q; g.q1 = -1;
+      for (int i = 0; i < 4; ++i) g.m[i] = m[i];
+      queue.push_back(g);
+      if (!layer_batch) flush();
+    }
+  }
+  void push_2q(int q0, int q1, const cplx* m) {
+    if (q0 < 0 || q1 < 0 || q0 >= ntot || q1 >= ntot) throw std::runtime_error("qubit index out of range");
+    if (std::abs(q0 - q1) != 1) throw std::runtime_error("two-qubit gate on non-adjacent qubits (run the nearest-neighbour pass first)");
+    if (reg_of(q0) != reg_of(q1)) throw std::runtime_error("two-qubit gate across registers");
+    QGate g;
+    g.q0 = q0; g.q1 = q1;
+    for (int i = 0; i < 16; ++i) g.m[i] = m[i];
+    if (fuse_1q && (has1q[q0] || has1q[q1])) {
+      // m' = m * (P_q0 (x) P_q1) in the (q0,q1) index order
+      cplx id[4] = {1, 0, 0, 1};
+      const cplx* a = has1q[q0] ? p1q[q0].data() : id;
+      const cplx* b = has1q[q1] ? p1q[q1].data() : id;
+      cplx kp[16];
+      for (int r0 = 0; r0 < 2; ++r0)
+        for (int r1 = 0; r1 < 2; ++r1)
+          for (int c0 = 0; c0 < 2; ++c0)
+            for (int c1 = 0; c1 < 2; ++c1) kp[(2 * r0 + r1) * 4 + 2 * c0 + c1] = a[2 * r0 + c0] * b[2 * r1 + c1];
+      for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+          cplx s = 0;
+          for (int k = 0; k < 4; ++k) s += m[4 * r + k] * kp[4 * k + c];
+          g.m[4 * r + c] = s;
+        }
+      has1q[q0] = has1q[q1] = 0;
+    }
+    queue.push_back(g);
+    if (!layer_batch) flush();
+  }
+
+  void flush() {
+    if (!queue.empty()) {
+      // dependency layering: a gate goes one layer after the last gate touching any of its sites
+      std::vector<int> level(ntot, -1);
+      std::vector<std::vector<int>> layers;
+      for (size_t i = 0; i < queue.size(); ++i) {
+        const QGate& g = queue[i];
+        int l = level[g.q0];
+        if (g.q1 >= 0) l = std::max(l, level[g.q1]);
+        ++l;
+        if ((int)layers.size() <= l) layers.resize(l + 1);
+        layers[l].push_back((int)i);
+        level[g.q0] = l;
+        if (g.q1 >= 0) level[g.q1] = l;
+      }
+      for (auto& L : layers) run_layer(L);
+      queue.clear();
+    }
+    // leftover fused single-qubit gates
+    std::vector<Gate1qProblem> p1;
+    for (int q = 0; q < ntot; ++q)
+      if (has1q[q]) {
+        Gate1qProblem p;
+        p.site = sites[q].d; p.dl = sites[q].dl; p.dr = sites[q].dr;
+        for (int i = 0; i < 4; ++i) p.m[i] = make_double2(p1q[q][i].real(), p1q[q][i].imag());
+        p1.push_back(p);
+        has1q[q] = 0;
+      }
+    run_1q(p1);
+  }
+
+  void run_1q(const std::vector<Gate1qProblem>& p1) {
+    if (p1.empty()) return;
+    size_t bytes = p1.size() * sizeof(Gate1qProblem);
+    ensure_ws(bytes + 256);
+    ws.reset();
+    size_t o = ws.reserve(bytes);
+    char* st = pinned(0, bytes);
+    CK(cudaStreamSynchronize(stream));   // staging reuse safety (1q-only flushes are rare)
+    memcpy(st, p1.data(), bytes);
+    CK(cudaMemcpyAsync(ws.base + o, st, bytes, cudaMemcpyHostToDevice, stream));
+    long mx = 0;
+    for (auto& p : p1) mx = std::max(mx, (long)p.dl * p.dr);
+    launch_gate1q((const Gate1qProblem*)(ws.base + o), (int)p1.size(), mx, stream);
+    nlaunch += 1;
+    n1q += p1.size();
+    CK(cudaGetLastError());
+  }
+
+  // ------------------------------------------------------------------ one dependency layer
+  void run_layer(const std::vector<int>& L) {
+    std::vector<Gate1qProblem> p1;
+    std::vector<int> g2;
+    for (int i : L) {
+      const QGate& g = queue[i];
+      if (g.q1 < 0) {
+        Gate1qProblem p;
+        p.site = sites[g.q0].d; p.dl = sites[g.q0].dl; p.dr = sites[g.q0].dr;
+        for (int k = 0; k < 4; ++k) p.m[k] = make_double2(g.m[k].real(), g.m[k].imag());
+        p1.push_back(p);
+      } else g2.push_back(i);
+    }
+    run_1q(p1);
+    if (g2.empty()) return;
+    const int B = (int)g2.size();
+    nlayers += 1;
+    n2q += B;
+
+    struct Dim { int lo, cl, ch, cr, M, N, tall, Mg, Ng; size_t oT, oG, oSig2, oSigma, oPerm, oSP, oSO, oKeep, oW; };
+    std::vector<Dim> D(B);
+    ws.reset();
+    // pass 1: sizes
+    for (int b = 0; b < B; ++b) {
+      const QGate& g = queue[g2[b]];
+      Dim& d = D[b];
+      d.lo = std::min(g.q0, g.q1);
+      d.cl = sites[d.lo].dl; d.ch = sites[d.lo].dr; d.cr = sites[d.lo + 1].dr;
+      d.M = 2 * d.cl; d.N = 2 * d.cr;
+      d.tall = d.M >= d.N;
+      d.Mg = d.tall ? d.M : d.N;
+      d.Ng = d.tall ? d.N : d.M;
+    }
+    // descriptor block first, then sigma block (contiguous for one read-back), then matrices
+    const size_t oGemm = ws.reserve(sizeof(GemmProblem) * B);
+    const size_t oJac = ws.reserve(sizeof(JacobiProblem) * B);
+    const size_t oTr = ws.reserve(sizeof(TruncProblem) * B);
+    const size_t oGat = ws.reserve(sizeof(GatherProblem) * B);
+    const size_t oGemm2 = ws.reserve(sizeof(GemmProblem) * B);
+    const size_t oFlags = ws.reserve(sizeof(int) * (2 * B + 4) + sizeof(double) * B + 16);   // dirty[B], done[B], remaining, pad, fro2[B]
+    const size_t oKeepBlk = ws.reserve((sizeof(int) + 2 * sizeof(double)) * B + 64);
+    size_t sig_total = 0;
+    for (int b = 0; b < B; ++b) sig_total += D[b].Ng;
+    const size_t oSigmaBlk = ws.reserve(sizeof(double) * sig_total);
+    {
+      size_t so = 0;
+      for (int b = 0; b < B; ++b) {
+        Dim& d = D[b];
+        d.oSigma = oSigmaBlk + sizeof(double) * so;
+        so += d.Ng;
+        d.oKeep = oKeepBlk + sizeof(int) * b;
+        d.oW = oKeepBlk + ((sizeof(int) * B + 15) & ~size_t(15)) + 2 * sizeof(double) * b;
+      }
+    }
+    for (int b = 0; b < B; ++b) {
+      Dim& d = D[b];
+      d.oSig2 = ws.reserve(sizeof(double) * d.Ng);
+      d.oPerm = ws.reserve(sizeof(int) * d.Ng);
+      d.oSP = ws.reserve(sizeof(double) * d.Ng);
+      d.oSO = ws.reserve(sizeof(double) * d.Ng);
+      d.oT = ws.reserve(sizeof(double2) * (size_t)d.Mg * d.Ng);
+      d.oG = ws.reserve(sizeof(double2) * (size_t)d.Mg * d.Ng);
+    }
+    const size_t total = ws.off;
+    ensure_ws(total);
+    char* wb = ws.base;
+
+    // pass 2: descriptors
+    const size_t descBytes = oFlags + sizeof(int) * (2 * B + 4) + sizeof(double) * B + 16 - oGemm;
+    char* st = pinned(0, descBytes);
+    memset(st, 0, descBytes);
+    GemmProblem* hG = (GemmProblem*)(st + (oGemm - oGemm));
+    JacobiProblem* hJ = (JacobiProblem*)(st + (oJac - oGemm));
+    TruncProblem* hT = (TruncProblem*)(st + (oTr - oGemm));
+    int max_tiles = 0, max_pairs = 1, max_steps = 1, maxMg = 1;
+    for (int b = 0; b < B; ++b) {
+      const QGate& g = queue[g2[b]];
+      const Dim& d = D[b];
+      GemmProblem& p = hG[b];
+      p.A = sites[d.lo].d; p.B = sites[d.lo + 1].d;
+      p.C = (double2*)(wb + d.oT); p.C2 = (double2*)(wb + d.oG);
+      p.M = d.cl; p.N = d.cr; p.K = d.ch;
+      p.lda = 2 * d.cl; p.ldb = d.ch; p.ldc = d.Mg;
+      p.b_col_stride = 1; p.b_col_off = 0;
+      p.mode = 1; p.conjT_out = d.tall ? 0 : 1; p.alpha = 1.0;
+      const bool q0lo = (g.q0 == d.lo);
+      for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+          // device index is 2*p_lo + p_hi; the gate's own index is 2*bit(q0)+bit(q1)  (ExaTnMpsVisitor.cpp:1492-1499)
+          const int rr = q0lo ? r : ((r & 1) << 1 | (r >> 1));
+          const int cc = q0lo ? c : ((c & 1) << 1 | (c >> 1));
+          p.gate[r * 4 + c] = make_double2(g.m[rr * 4 + cc].real(), g.m[rr * 4 + cc].imag());
+        }
+      max_tiles = std::max(max_tiles, gemm_tiles(p.M, p.N, 1));
+      JacobiProblem& j = hJ[b];
+      j.G = (double2*)(wb + d.oG); j.M = d.Mg; j.N = d.Ng; j.ldg = d.Mg;
+      j.nb = (d.Ng + 7) / 8;
+      j.nbe = (j.nb == 1) ? 1 : ((j.nb + 1) & ~1);
+      max_pairs = std::max(max_pairs, j.nb == 1 ? 1 : j.nbe / 2);
+      max_steps = std::max(max_steps, j.nb == 1 ? 1 : j.nbe - 1);
+      maxMg = std::max(maxMg, d.Mg);
+      TruncProblem& t = hT[b];
+      t.G = j.G; t.M = d.Mg; t.N = d.Ng; t.ldg = d.Mg; t.tall = d.tall;
+      t.sig2 = (double*)(wb + d.oSig2); t.sigma = (double*)(wb + d.oSigma); t.perm = (int*)(wb + d.oPerm);
+      t.scaleP = (double*)(wb + d.oSP); t.scaleO = (double*)(wb + d.oSO);
+      t.keep = (int*)(wb + d.oKeep); t.weights = (double*)(wb + d.oW);
+    }
+    CK(cudaMemcpyAsync(wb + oGemm, st, descBytes, cudaMemcpyHostToDevice, stream));   // flags zeroed too
+    int* d_dirty = (int*)(wb + oFlags);
+    int* d_done = d_dirty + B;
+    int* d_rem = d_done + B;
+    double* d_fro2 = (double*)(wb + oFlags + ((sizeof(int) * (2 * B + 4) + 7) & ~size_t(7)));
+
+    if (profile) CK(cudaEventRecord(ev[0], stream));
+    launch_gemm((const GemmProblem*)(wb + oGemm), B, max_tiles, 0, stream);
+    nlaunch += 1;
+    if (profile) CK(cudaEventRecord(ev[1], stream));
+
+    // ---- Jacobi sweeps
+    const double eps = 2.220446049250313e-16;
+    const double tol = jacobi_tol > 0 ? jacobi_tol : std::sqrt((double)maxMg) * eps;
+    const double tol2 = tol * tol;
+    const double ntol = null_tol > 0 ? null_tol : 10.0 * tol;   // numerically-null threshold relative to sigma_max
+    const double dead2 = ntol * ntol;
+    int* h_rem = (int*)pinned_rb(sizeof(int) * (B + 4) + sizeof(double) * (2 * B + sig_total) + 256);
+    launch_fro2((const JacobiProblem*)(wb + oJac), B, d_fro2, stream);
+    nlaunch += 1;
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+      for (int s = 0; s < max_steps; ++s) launch_jacobi_step((const JacobiProblem*)(wb + oJac), B, max_pairs, s, tol2, dead2, d_fro2, d_dirty, d_done, stream);
+      launch_jacobi_check(B, d_dirty, d_done, d_rem, stream);
+      nlaunch += max_steps + 1;
+      CK(cudaMemcpyAsync(h_rem, d_rem, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      if (*h_rem == 0) { ++sweep; break; }
+    }
+    nsweeps += sweep;
+    if (profile) CK(cudaEventRecord(ev[2], stream));
+
+    // ---- sort / truncate, read back kept dims + singular values
+    launch_trunc((const TruncProblem*)(wb + oTr), B, cutoff, cutoff_on_sqrt, max_bond, gauge, renorm, ntol, stream);
+    nlaunch += 1;
+    const size_t keepBlkBytes = ((sizeof(int) * B + 15) & ~size_t(15)) + 2 * sizeof(double) * B;
+    char* rb = (char*)h_rem;
+    CK(cudaMemcpyAsync(rb, wb + oKeepBlk, keepBlkBytes, cudaMemcpyDeviceToHost, stream));
+    char* rbSig = rb + ((keepBlkBytes + 15) & ~size_t(15));
+    CK(cudaMemcpyAsync(rbSig, wb + oSigmaBlk, sizeof(double) * sig_total, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const int* h_keep = (const int*)rb;
+    const double* h_w = (const double*)(rb + ((sizeof(int) * B + 15) & ~size_t(15)));
+    const double* h_sig = (const double*)rbSig;
+
+    // ---- write-back
+    const size_t gaBytes = (sizeof(GatherProblem) * B + 255) & ~size_t(255);   // GemmProblem needs 16-byte alignment
+    char* st2 = pinned(1, gaBytes + sizeof(GemmProblem) * B);
+    GatherProblem* hGa = (GatherProblem*)st2;
+    GemmProblem* hG2 = (GemmProblem*)(st2 + gaBytes);
+    memset(st2, 0, gaBytes + sizeof(GemmProblem) * B);
+    int max_rows = 1, max_keep = 1, max_tiles2 = 1;
+    size_t so = 0;
+    for (int b = 0; b < B; ++b) {
+      const Dim& d = D[b];
+      const int keep = h_keep[b];
+      if (keep < 1 || keep > d.Ng) throw std::runtime_error("internal: bad kept bond dimension");
+      if (h_w[2 * b] > 0) discarded += (h_w[2 * b] - h_w[2 * b + 1]) / h_w[2 * b];
+      sv[d.lo].assign(h_sig + so, h_sig + so + keep);
+      so += d.Ng;
+      ensure_site(d.lo, d.cl, keep, false);
+      ensure_site(d.lo + 1, keep, d.cr, false);
+      GatherProblem& ga = hGa[b];
+      GemmProblem& p = hG2[b];
+      ga.G = (const double2*)(wb + d.oG); ga.perm = (const int*)(wb + d.oPerm); ga.scale = (const double*)(wb + d.oSP);
+      ga.M = d.Mg; ga.keep = keep; ga.ldg = d.Mg;
+      p.alpha = 1.0; p.mode = 0; p.conjT_out = 0; p.b_col_stride = 1; p.b_col_off = 0;
+      if (d.tall) {
+        // lo = G[:,perm] * sP  (M x keep);  hi = diag(sO) * G[:,perm]^H * theta  (keep x N)
+        ga.out = sites[d.lo].d; ga.ldo = d.M; ga.conjT = 0;
+        p.A = (const double2*)(wb + d.oG); p.lda = d.Mg; p.a_gather = (const int*)(wb + d.oPerm);
+        p.B = (const double2*)(wb + d.oT); p.ldb = d.Mg;
+        p.C = sites[d.lo + 1].d; p.ldc = keep;
+        p.M = keep; p.N = d.N; p.K = d.Mg;
+        p.row_scale = (const double*)(wb + d.oSO);
+      } else {
+        // hi = (G[:,perm] * sP)^H  (keep x N);  lo = theta * G[:,perm] * diag(sO) = T^H G[:,perm] diag(sO)  (M x keep)
+        ga.out = sites[d.lo + 1].d; ga.ldo = keep; ga.conjT = 1;
+        p.A = (const double2*)(wb + d.oT); p.lda = d.Mg;
+        p.B = (const double2*)(wb + d.oG); p.ldb = d.Mg; p.b_gather = (const int*)(wb + d.oPerm);
+        p.C = sites[d.lo].d; p.ldc = d.M;
+        p.M = d.M; p.N = keep; p.K = d.Mg;
+        p.col_scale = (const double*)(wb + d.oSO);
+      }
+      max_rows = std::max(max_rows, d.Mg);
+      max_keep = std::max(max_keep, keep);
+      max_tiles2 = std::max(max_tiles2, gemm_tiles(p.M, p.N, 0));
+    }
+    CK(cudaMemcpyAsync(wb + oGat, st2, sizeof(GatherProblem) * B, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(wb + oGemm2, st2 + gaBytes, sizeof(GemmProblem) * B, cudaMemcpyHostToDevice, stream));
+    launch_gather((const GatherProblem*)(wb + oGat), B, max_rows, max_keep, stream);
+    launch_gemm((const GemmProblem*)(wb + oGemm2), B, max_tiles2, 1, stream);
+    nlaunch += 2;
+    CK(cudaGetLastError());
+    if (profile) {
+      CK(cudaEventRecord(ev[3], stream));
+      CK(cudaEventSynchronize(ev[3]));
+      float a = 0, b2 = 0, c = 0;
+      CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+      CK(cudaEventElapsedTime(&b2, ev[1], ev[2]));
+      CK(cudaEventElapsedTime(&c, ev[2], ev[3]));
+      ms_theta += a; ms_svd += b2; ms_wb += c;
+    }
+  }
+
+  // ------------------------------------------------------------------ observables
+  // <psi| prod_k diag(w[k][0], w[k][1]) |psi> over the sites [s0, s1) by a left-to-right transfer sweep.
+  // If envs != nullptr the environment before each site is kept there (device pointers into the arena).
+  struct EnvBufs { std::vector<double2*> e; };
+
+  void left_step(const SiteBuf& S, const double2* E, double2* F, double2* Eout, double w0, double w1) {
+    const int dl = S.dl, dr = S.dr;
+    for (int p = 0; p < 2; ++p) {
+      GemmProblem g;
+      memset(&g, 0, sizeof(g));
+      g.A = E; g.lda = dl; g.B = S.d + (size_t)p * dl; g.ldb = 2 * dl; g.C = F + (size_t)p * dl; g.ldc = 2 * dl;
+      g.M = dl; g.N = dr; g.K = dl; g.b_col_stride = 1; g.alpha = p ? w1 : w0;
+      launch_gemm1(g, 0, stream);
+    }
+    GemmProblem g;
+    memset(&g, 0, sizeof(g));
+    g.A = S.d; g.lda = 2 * dl; g.B = F; g.ldb = 2 * dl; g.C = Eout; g.ldc = dr;
+    g.M = dr; g.N = dr; g.K = 2 * dl; g.b_col_stride = 1; g.alpha = 1.0;
+    launch_gemm1(g, 1, stream);
+    nlaunch += 3;
+  }
+  // R_k[a,a'] = sum_{p,c,c'} A[a,p,c] R[c,c'] conj(A[a',p,c'])
+  void right_step(const SiteBuf& S, const double2* R, double2* H, double2* Rout) {
+    const int dl = S.dl, dr = S.dr;
+    for (int p = 0; p < 2; ++p) {
+      GemmProblem g;
+      memset(&g, 0, sizeof(g));
+      g.A = S.d + (size_t)p * dl; g.lda = 2 * dl; g.B = R; g.ldb = dr; g.C = H + (size_t)p * dl; g.ldc = 2 * dl;
+      g.M = dl; g.N = dr; g.K = dr; g.b_col_stride = 1; g.alpha = 1.0;
+      launch_gemm1(g, 0, stream);
+    }
+    GemmProblem g;
+    memset(&g, 0, sizeof(g));
+    g.A = H; g.lda = dl; g.B = S.d; g.ldb = dl; g.C = Rout; g.ldc = dl;
+    g.M = dl; g.N = dl; g.K = 2 * dr; g.b_col_stride = 1; g.alpha = 1.0;
+    launch_gemm1(g, 2, stream);
+    nlaunch += 3;
+  }
+
+  size_t max_env_elems(int s0, int s1) const {
+    size_t m = 1;
+    for (int k = s0; k < s1; ++k) m = std::max(m, (size_t)sites[k].dr * sites[k].dr);
+    return m;
+  }
+  size_t max_site_elems(int s0, int s1) const {
+    size_t m = 2;
+    for (int k = s0; k < s1; ++k) m = std::max(m, (size_t)2 * sites[k].dl * sites[k].dr);
+    return m;
+  }
+
+  cplx sweep_weights(int reg, const std::vector<std::array<double, 2>>& w) {
+    flush();
+    const int s0 = reg * nq, s1 = s0 + nq;
+    const size_t me = max_env_elems(s0, s1), ms = max_site_elems(s0, s1);
+    ws.reset();
+    const size_t oE0 = ws.reserve(me * 16), oE1 = ws.reserve(me * 16), oF = ws.reserve(ms * 16);
+    ensure_ws(ws.off);
+    double2* E[2] = {(double2*)(ws.base + oE0), (double2*)(ws.base + oE1)};
+    double2* F = (double2*)(ws.base + oF);
+    const cplx one(1, 0);
+    CK(cudaMemcpyAsync(E[0], &one, 16, cudaMemcpyHostToDevice, stream));
+    int cur = 0;
+    for (int k = s0; k < s1; ++k) {
+      left_step(sites[k], E[cur], F, E[cur ^ 1], w[k - s0][0], w[k - s0][1]);
+      cur ^= 1;
+    }
+    cplx out;
+    CK(cudaMemcpyAsync(&out, E[cur], 16, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    return out;
+  }
+
+  // left environments L[k] (before site s0+k, k = 0..n) and right environments R[k] (after site s0+k-1)
+  void build_envs(int reg, std::vector<double2*>& Lv, std::vector<double2*>& Rv, double2*& F, double2*& Etmp, double2*& Etmp2, double2*& scal) {
+    flush();
+    const int s0 = reg * nq, n = nq;
+    ws.reset();
+    std::vector<size_t> oL(n + 1), oR(n + 1);
+    for (int k = 0; k <= n; ++k) {
+      const size_t d = (k == 0) ? 1 : sites[s0 + k - 1].dr;
+      oL[k] = ws.reserve(d * d * 16);
+      oR[k] = ws.reserve(d * d * 16);
+    }
+    const size_t oF = ws.reserve(max_site_elems(s0, s0 + n) * 16);
+    const size_t oT = ws.reserve(max_env_elems(s0, s0 + n) * 16);
+    const size_t oT2 = ws.reserve(max_env_elems(s0, s0 + n) * 16);
+    const size_t oS = ws.reserve(16 * (size_t)(n + 8));
+    ensure_ws(ws.off);
+    Lv.resize(n + 1); Rv.resize(n + 1);
+    for (int k = 0; k <= n; ++k) { Lv[k] = (double2*)(ws.base + oL[k]); Rv[k] = (double2*)(ws.base + oR[k]); }
+    F = (double2*)(ws.base + oF);
+    Etmp = (double2*)(ws.base + oT);
+    Etmp2 = (double2*)(ws.base + oT2);
+    scal = (double2*)(ws.base + oS);
+    const cplx one(1, 0);
+    CK(cudaMemcpyAsync(Lv[0], &one, 16, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(Rv[n], &one, 16, cudaMemcpyHostToDevice, stream));
+    for (int k = 0; k < n; ++k) left_step(sites[s0 + k], Lv[k], F, Lv[k + 1], 1.0, 1.0);
+    for (int k = n - 1; k >= 0; --k) right_step(sites[s0 + k], Rv[k + 1], F, Rv[k]);
+  }
+
+  void expval_z_all(int reg, double* out) {
+    std::vector<double2*> Lv, Rv;
+    double2 *F, *Et, *Et2, *scal;
+    build_envs(reg, Lv, Rv, F, Et, Et2, scal);
+    const int s0 = reg * nq;
+    for (int k = 0; k < nq; ++k) {
+      left_step(sites[s0 + k], Lv[k], F, Et, 1.0, -1.0);
+      launch_trace_pair(Et, Rv[k + 1], sites[s0 + k].dr, scal + k, stream);
+      nlaunch += 1;
+    }
+    std::vector<cplx> h(nq);
+    CK(cudaMemcpyAsync(h.data(), scal, 16 * (size_t)nq, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    for (int k = 0; k < nq; ++k) out[k] = h[k].real();
+  }
+
+  void expval_zz_pairs(int reg, int np, const int* qi, const int* qj, double* out) {
+    std::vector<double2*> Lv, Rv;
+    double2 *F, *Et, *Et2, *scal;
+    build_envs(reg, Lv, Rv, F, Et, Et2, scal);
+    const int s0 = reg * nq;
+    std::vector<cplx> h(1);
+    for (int t = 0; t < np; ++t) {
+      int i = std::min(qi[t], qj[t]), j = std::max(qi[t], qj[t]);
+      if (i < 0 || j >= nq) throw std::runtime_error("qubit index out of range");
+      const double2* src;
+      int dlast;
+      if (i == j) { src = Lv[nq]; dlast = 1; launch_trace_pair(src, Rv[nq], 1, scal, stream); }
+      else {
+        left_step(sites[s0 + i], Lv[i], F, Et, 1.0, -1.0);
+        double2* cur = Et; double2* nxt = Et2;
+        for (int k = i + 1; k < j; ++k) { left_step(sites[s0 + k], cur, F, nxt, 1.0, 1.0); std::swap(cur, nxt); }
+        left_step(sites[s0 + j], cur, F, nxt, 1.0, -1.0);
+        dlast = sites[s0 + j].dr;
+        launch_trace_pair(nxt, Rv[j + 1], dlast, scal, stream);
+      }
+      nlaunch += 1;
+      CK(cudaMemcpyAsync(h.data(), scal, 16, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      out[t] = h[0].real();
+    }
+    CK(cudaGetLastError());
+  }
+
+  // amplitudes with open legs: bits[k] in {0,1,-1}
+  void amplitude(int reg, const int8_t* bits, std::vector<cplx>& out) {
+    flush();
+    const int s0 = reg * nq;
+    int nopen = 0;
+    for (int k = 0; k < nq; ++k) if (bits[k] < 0) ++nopen;
+    if (nopen > 30) throw std::runtime_error("too many open legs");
+    // buffer size: rows * max(dr) growing; bound by 2^nopen * max bond * 2
+    size_t maxd = 1;
+    for (int k = s0; k < s0 + nq; ++k) maxd = std::max(maxd, (size_t)sites[k].dr);
+    const size_t elems = ((size_t)1 << nopen) * maxd * 2;
+    ws.reset();
+    const size_t o0 = ws.reserve(elems * 16), o1 = ws.reserve(elems * 16);
+    ensure_ws(ws.off);
+    double2* S[2] = {(double2*)(ws.base + o0), (double2*)(ws.base + o1)};
+    const cplx one(1, 0);
+    CK(cudaMemcpyAsync(S[0], &one, 16, cudaMemcpyHostToDevice, stream));
+    int cur = 0;
+    size_t rows = 1;
+    for (int k = 0; k < nq; ++k) {
+      const SiteBuf& sb = sites[s0 + k];
+      GemmProblem g;
+      memset(&g, 0, sizeof(g));
+      g.A = S[cur]; g.lda = (int)rows; g.B = sb.d; g.ldb = sb.dl; g.C = S[cur ^ 1]; g.ldc = (int)rows;
+      g.M = (int)rows; g.K = sb.dl; g.alpha = 1.0;
+      if (bits[k] < 0) { g.N = 2 * sb.dr; g.b_col_stride = 1; g.b_col_off = 0; }
+      else { g.N = sb.dr; g.b_col_stride = 2; g.b_col_off = bits[k]; }
+      launch_gemm1(g, 0, stream);
+      nlaunch += 1;
+      if (bits[k] < 0) rows *= 2;
+      cur ^= 1;
+    }
+    out.resize(rows);
+    CK(cudaMemcpyAsync(out.data(), S[cur], 16 * rows, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+  }
+};
+
+// =================================================================================== C ABI
+#define API_BEGIN(h)              \
+  if (!(h)) return 1;             \
+  try {                           \
+    CK(cudaSetDevice((h)->device));
+#define API_END(h)                \
+    return 0;                     \
+  } catch (const std::exception& e) { \
+    (h)->err = e.what();          \
+    return 2;                     \
+  } catch (...) {                 \
+    (h)->err = "unknown error";   \
+    return 3;                     \
+  }
+
+extern "C" {
+
+int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, int gauge, int device, uint64_t seed,
+               mps_handle_t* out) {
+  if (!out) return 1;
+  *out = nullptr;
+  mps_b200_handle* h = nullptr;
+  try {
+    if (getenv("MPS_B200_BACKTRACE")) signal(SIGSEGV, segv_handler);
+    if (n_qubits < 1 || n_registers < 1) throw std::runtime_error("n_qubits and n_registers must be >= 1");
+    if (gauge < 0 || gauge > 2) throw std::runtime_error("unknown gauge");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw std::runtime_error(std::string("no CUDA device available (this engine has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) throw std::runtime_error("bad device index");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) throw std::runtime_error("libmps_b200 is built for sm_100a (Blackwell) only");
+    h = new mps_b200_handle;
+    h->nq = n_qubits; h->nreg = n_registers; h->ntot = n_qubits * n_registers;
+    if (max_bond > 0) h->max_bond = max_bond;
+    if (svd_cutoff >= 0) h->cutoff = svd_cutoff;
+    h->gauge = gauge; h->device = device;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+    h->sites.resize(h->ntot);
+    h->has1q.assign(h->ntot, 0);
+    h->p1q.resize(h->ntot);
+    h->sv.assign(std::max(h->ntot - 1, 1), std::vector<double>{1.0});
+    if (seed) h->rng.seed(seed);
+    else { std::random_device rd; h->rng.seed(rd()); }   // RandomEngine.hpp:39-42
+    h->reset_state();
+    *out = h;
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    delete h;
+    return 2;
+  }
+}
+
+int mps_destroy(mps_handle_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto& s : h->sites) if (s.d) cudaFree(s.d);
+  if (h->ws.base) cudaFree(h->ws.base);
+  for (int i = 0; i < 2; ++i) if (h->pin[i]) cudaFreeHost(h->pin[i]);
+  if (h->pin_rb) cudaFreeHost(h->pin_rb);
+  for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+const char* mps_last_error(mps_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mps_reset(mps_handle_t h) { API_BEGIN(h) h->reset_state(); API_END(h) }
+
+int mps_set_option(mps_handle_t h, const char* key, double value) {
+  API_BEGIN(h)
+  std::string k(key);
+  if (k == "cutoff_on_sqrt") h->cutoff_on_sqrt = value != 0;
+  else if (k == "fuse_1q") { h->flush(); h->fuse_1q = value != 0; }
+  else if (k == "renormalize") h->renorm = value != 0;
+  else if (k == "jacobi_tol") h->jacobi_tol = value;
+  else if (k == "null_tol") h->null_tol = value;
+  else if (k == "jacobi_max_sweeps") h->max_sweeps = (int)value;
+  else if (k == "profile") h->profile = value != 0;
+  else if (k == "layer_batch") { h->flush(); h->layer_batch = value != 0; }
+  else if (k == "max_bond") h->max_bond = value > 0 ? (int)value : INT_MAX - 1;
+  else if (k == "svd_cutoff") h->cutoff = value >= 0 ? value : DBL_MIN;
+  else if (k == "gauge") h->gauge = (int)value;
+  else throw std::runtime_error("unknown option: " + k);
+  API_END(h)
+}
+
+int mps_apply_1q(mps_handle_t h, int q, const double m[8]) {
+  API_BEGIN(h) h->push_1q(q, reinterpret_cast<const cplx*>(m)); API_END(h)
+}
+int mps_apply_2q(mps_handle_t h, int q0, int q1, const double m[32]) {
+  API_BEGIN(h) h->push_2q(q0, q1, reinterpret_cast<const cplx*>(m)); API_END(h)
+}
+int mps_apply_layer(mps_handle_t h, int count, const int* q0, const int* q1, const double* mats) {
+  API_BEGIN(h)
+  for (int i = 0; i < count; ++i) h->push_2q(q0[i], q1[i], reinterpret_cast<const cplx*>(mats + 32 * (size_t)i));
+  API_END(h)
+}
+int mps_flush(mps_handle_t h) { API_BEGIN(h) h->flush(); API_END(h) }
+int mps_sync(mps_handle_t h) {
+  API_BEGIN(h)
+  h->flush();
+  CK(cudaStreamSynchronize(h->stream));
+  API_END(h)
+}
+
+int mps_norm(mps_handle_t h, int reg, double* out) {
+  API_BEGIN(h)
+  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
+  std::vector<std::array<double, 2>> w(h->nq, {1.0, 1.0});
+  *out = h->sweep_weights(reg, w).real();
+  API_END(h)
+}
+int mps_expval_z(mps_handle_t h, int reg, int nq, const int* qubits, double* out) {
+  API_BEGIN(h)
+  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
+  std::vector<std::array<double, 2>> w(h->nq, {1.0, 1.0});
+  for (int i = 0; i < nq; ++i) {
+    if (qubits[i] < 0 || qubits[i] >= h->nq) throw std::runtime_error("qubit index out of range");
+    w[qubits[i]][1] = -w[qubits[i]][1];
+  }
+  *out = h->sweep_weights(reg, w).real();
+  API_END(h)
+}
+int mps_expval_z_all(mps_handle_t h, int reg, double* out_n) {
+  API_BEGIN(h)
+  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
+  h->expval_z_all(reg, out_n);
+  API_END(h)
+}
+int mps_expval_zz_pairs(mps_handle_t h, int reg, int npairs, const int* qi, const int* qj, double* out) {
+  API_BEGIN(h)
+  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
+  h->expval_zz_pairs(reg, npairs, qi, qj, out);
+  API_END(h)
+}
+int mps_amplitude(mps_handle_t h, int reg, const int8_t* bits, double* out, size_t* len) {
+  API_BEGIN(h)
+  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
+  std::vector<cplx> v;
+  h->amplitude(reg, bits, v);
+  if (out) memcpy(out, v.data(), 16 * v.size());
+  if (len) *len = v.size();
+  API_END(h)
+}
+int mps_statevector(mps_handle_t h, int reg, double* out) {
+  API_BEGIN(h)
+  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
+  if (h->nq > 30) throw std::runtime_error("state vector limited to 30 qubits");
+  std::vector<int8_t> bits(h->nq, -1);
+  std::vector<cplx> v;
+  h->amplitude(reg, bits.data(), v);
+  memcpy(out, v.data(), 16 * v.size());
+  API_END(h)
+}
+
+int mps_measure(mps_handle_t h, int q) {
+  API_BEGIN(h)
+  if (q < 0 || q >= h->nq) throw std::runtime_error("qubit index out of range");
+  h->measure.push_back(q);
+  API_END(h)
+}
+int mps_clear_measure(mps_handle_t h) { API_BEGIN(h) h->measure.clear(); API_END(h) }
+int mps_seed(mps_handle_t h, uint64_t seed) { API_BEGIN(h) h->rng.seed(seed); API_END(h) }
+
+int mps_sample(mps_handle_t h, int reg, int shots, char* out, int* n_out) {
+  API_BEGIN(h)
+  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
+  const int nm = (int)h->measure.size();
+  int produced = 0;
+  if (nm > 0 && shots > 0) {
+    if (h->nq < 20) {   // MAX_NUMBER_QUBITS_FOR_STATE_VEC, ExaTnMpsVisitor.cpp:55
+      // GenerateSamples (GateMatrixAlgebra.hpp:125-156): draw, sort, walk the CDF in state-index order
+      std::vector<int8_t> bits(h->nq, -1);
+      std::vector<cplx> sv;
+      h->amplitude(reg, bits.data(), sv);
+      std::vector<double> rs;
+      rs.reserve(shots + 1);
+      for (int i = 0; i < shots; ++i) rs.push_back(std::uniform_real_distribution<double>(0.0, 1.0)(h->rng));
+      std::sort(rs.begin(), rs.end());
+      double csum = 0.0;
+      size_t m = 0;
+      for (size_t k = 0; k < sv.size(); ++k) {
+        csum += std::norm(sv[k]);
+        while (m < (size_t)shots && rs[m] < csum) {
+          for (int i = 0; i < nm; ++i) out[m * nm + i] = (k & (1ULL << h->measure[i])) ? '1' : '0';
+          ++m;
+        }
+      }
+      produced = (int)m;
+    } else {
+      // getMeasureSample (ExaTnMpsVisitor.cpp:2211-2364): conditional single-qubit RDM diagonals in Measure order
+      for (int s = 0; s < shots; ++s) {
+        std::vector<int> res;
+        std::vector<double> probs;
+        for (int mi = 0; mi < nm; ++mi) {
+          const int q = h->measure[mi];
+          double pb[2];
+          for (int b = 0; b < 2; ++b) {
+            std::vector<std::array<double, 2>> w(h->nq, {1.0, 1.0});
+            for (size_t j = 0; j < res.size(); ++j) {
+              const int qq = h->measure[j];
+              w[qq][res[j]] *= 1.0 / probs[j];
+              w[qq][1 - res[j]] = 0.0;
+            }
+            w[q][1 - b] = 0.0;
+            pb[b] = h->sweep_weights(reg, w).real();
+          }
+          const double PROB_EPS = 1e-12;
+          const double p0 = std::fabs(pb[0]) < PROB_EPS ? 0.0 : pb[0];
+          const double p1 = std::fabs(pb[1]) < PROB_EPS ? 0.0 : pb[1];
+          const double r = std::uniform_real_distribution<double>(0.0, 1.0)(h->rng);
+          const int bit = (r <= p0) ? 0 : 1;
+          res.push_back(bit);
+          probs.push_back(bit == 0 ? p0 : p1);
+          out[(size_t)s * nm + mi] = bit ? '1' : '0';
+        }
+        ++produced;
+      }
+    }
+  }
+  if (n_out) *n_out = produced;
+  API_END(h)
+}
+
+int mps_bond_dims(mps_handle_t h, int* out) {
+  API_BEGIN(h)
+  h->flush();
+  for (int k = 0; k + 1 < h->ntot; ++k) out[k] = h->sites[k].dr;
+  API_END(h)
+}
+int mps_singular_values(mps_handle_t h, int bond, double* out, int cap, int* count) {
+  API_BEGIN(h)
+  h->flush();
+  if (bond < 0 || bond >= h->ntot - 1) throw std::runtime_error("bad bond index");
+  const auto& v = h->sv[bond];
+  const int c = std::min<int>(cap, (int)v.size());
+  for (int i = 0; i < c; ++i) out[i] = v[i];
+  if (count) *count = (int)v.size();
+  API_END(h)
+}
+int mps_discarded_weight(mps_handle_t h, double* out) {
+  API_BEGIN(h)
+  h->flush();
+  *out = h->discarded;
+  API_END(h)
+}
+int mps_get_site(mps_handle_t h, int k, double* out, int shape[3]) {
+  API_BEGIN(h)
+  h->flush();
+  if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
+  const SiteBuf& s = h->sites[k];
+  shape[0] = s.dl; shape[1] = 2; shape[2] = s.dr;
+  if (out) {
+    CK(cudaMemcpyAsync(out, s.d, (size_t)2 * s.dl * s.dr * 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  API_END(h)
+}
+int mps_set_site(mps_handle_t h, int k, const double* in, int dl, int dr) {
+  API_BEGIN(h)
+  h->flush();
+  if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
+  h->ensure_site(k, dl, dr, false);
+  CK(cudaMemcpyAsync(h->sites[k].d, in, (size_t)2 * dl * dr * 16, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  API_END(h)
+}
+int mps_site_device_ptr(mps_handle_t h, int k, void** dptr, int shape[3]) {
+  API_BEGIN(h)
+  h->flush();
+  CK(cudaStreamSynchronize(h->stream));
+  if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
+  const SiteBuf& s = h->sites[k];
+  *dptr = s.d;
+  shape[0] = s.dl; shape[1] = 2; shape[2] = s.dr;
+  API_END(h)
+}
+int mps_resize_site(mps_handle_t h, int k, int dl, int dr, void** dptr) {
+  API_BEGIN(h)
+  h->flush();
+  if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
+  h->ensure_site(k, dl, dr, false);
+  CK(cudaStreamSynchronize(h->stream));
+  *dptr = h->sites[k].d;
+  API_END(h)
+}
+int mps_stats(mps_handle_t h, double* out, int cap) {
+  API_BEGIN(h)
+  const double v[8] = {h->n2q, h->n1q, h->nlayers, h->nsweeps, h->nlaunch, h->ms_theta, h->ms_svd, h->ms_wb};
+  for (int i = 0; i < cap && i < 8; ++i) out[i] = v[i];
+  API_END(h)
+}
+
+}  // extern "C"

@@ -1,0 +1,417 @@
+// Batched one-sided (Hestenes) block-Jacobi SVD for the 2-qubit gate step, complex128, sm_100a.
+//
+// Replaces exatn::decomposeTensorSVDLRSync (LAPACK zgesvd/zgesdd inside TAL-SH) at
+// ExaTnMpsVisitor.cpp:1619-1627 and the partial-norm / slice truncation of :2366-2536.
+//
+// One launch = one "step" of a round-robin tournament over 8-column blocks; each CTA owns a pair of
+// blocks (16 columns) of one matrix of the batch:
+//   phase A  W = X^H X (16x16 Hermitian Gram matrix) on the FP64 tensor cores (DMMA) streaming the 16
+//            columns from L2 -- the A- and B-fragments of X^T X coincide, so each element is loaded once;
+//   phase B  one cyclic sweep of 2x2 Hermitian Jacobi rotations on W in shared memory (warp 0,
+//            8 disjoint pairs per round), accumulating the 16x16 unitary Q;
+//   phase C  X <- X Q on DMMA, written back in place.
+// A CTA whose fresh Gram matrix is already orthogonal to tolerance does nothing; a matrix is converged
+// after a full tournament without any rotation.  V is never accumulated: the other factor comes from
+// one GEMM against the saved theta (see engine.cu), which is what keeps the kernel at 16 columns/CTA.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace mpsb200 {
+namespace {
+
+constexpr int JT = 128;     // threads per CTA (4 warps)
+constexpr int WLD = 17;     // padded leading dimension of the 16x16 shared matrices
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {   // conj(a) * b
+  return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 rmul(double r, double2 a) { return make_double2(r * a.x, r * a.y); }
+
+__global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem* __restrict__ probs, int step, double tol2, double dead2,
+                                                            const double* __restrict__ fro2, int* __restrict__ dirty,
+                                                            const int* __restrict__ done) {
+  const int mat = blockIdx.y;
+  if (done[mat]) return;
+  const JacobiProblem P = probs[mat];
+  const int npairs = (P.nb == 1) ? 1 : P.nbe / 2;
+  const int pi = blockIdx.x;
+  if (pi >= npairs) return;
+  int blkA = 0, blkB = -1;
+  if (P.nb > 1) {
+    const int nm1 = P.nbe - 1;
+    const int s = step % nm1;
+    if (pi == 0) { blkA = nm1; blkB = s; }
+    else { blkA = (s + pi) % nm1; blkB = (s + nm1 - pi) % nm1; }
+    if (blkA >= P.nb) blkA = -1;
+    if (blkB >= P.nb) blkB = -1;
+    if (blkA < 0) { blkA = blkB; blkB = -1; }
+    if (blkA < 0) return;
+  }
+  const int M = P.M, N = P.N, ldg = P.ldg;
+  double2* __restrict__ G = P.G;
+  // columns whose squared norm is below dead_abs (<= (null_tol * sigma_max)^2) are numerically null: they are zeroed at
+  // write-back and never rotated, so rank-deficient thetas do not spend sweeps orthogonalising rounding noise
+  const double dead_abs = dead2 * fro2[mat] / (double)N;
+
+  __shared__ int s_cols[16];
+  __shared__ double s_red[4][7][64];
+  __shared__ double2 sW[16 * WLD];
+  __shared__ double2 sQ[16 * WLD];
+  __shared__ double s_rc[8];
+  __shared__ double2 s_rs[8];
+  __shared__ int s_rp[8], s_rq[8];
+  __shared__ int s_need;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 16) {
+    int c;
+    if (tid < 8) c = blkA * 8 + tid;
+    else c = (blkB >= 0) ? blkB * 8 + (tid - 8) : N;
+    s_cols[tid] = (c < N) ? c : -1;
+  }
+  if (tid == 0) s_need = 0;
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase A: Gram matrix on DMMA
+  {
+    const int slot = lane >> 2, rsub = lane & 3;
+    const int c0 = s_cols[slot], c1 = s_cols[8 + slot];
+    const double2* p0 = (c0 >= 0) ? G + (size_t)ldg * c0 : nullptr;
+    const double2* p1 = (c1 >= 0) ? G + (size_t)ldg * c1 : nullptr;
+    double w00[2] = {0, 0}, m00[2] = {0, 0}, w11[2] = {0, 0}, m11[2] = {0, 0}, w01[2] = {0, 0}, p01[2] = {0, 0}, q01[2] = {0, 0};
+    const int nch = (M + 3) >> 2;
+    constexpr int UN = 4;
+    for (int base = warp * UN; base < nch; base += 4 * UN) {
+      double2 x0[UN], x1[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int row = 4 * (base + u) + rsub;
+        const bool ok = row < M;
+        x0[u] = (ok && p0) ? p0[row] : make_double2(0.0, 0.0);
+        x1[u] = (ok && p1) ? p1[row] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        dmma884(w00[0], w00[1], x0[u].x, x0[u].x);
+        dmma884(m00[0], m00[1], x0[u].x, x0[u].y);
+        dmma884(w11[0], w11[1], x1[u].x, x1[u].x);
+        dmma884(m11[0], m11[1], x1[u].x, x1[u].y);
+        dmma884(w01[0], w01[1], x0[u].x, x1[u].x);
+        dmma884(p01[0], p01[1], x0[u].x, x1[u].y);
+        dmma884(q01[0], q01[1], x0[u].y, x1[u].x);
+        dmma884(w00[0], w00[1], x0[u].y, x0[u].y);
+        dmma884(w11[0], w11[1], x1[u].y, x1[u].y);
+        dmma884(w01[0], w01[1], x0[u].y, x1[u].y);
+      }
+    }
+    // C fragment: element (row = lane>>2, col = 2*(lane&3)+e)
+    const int e0 = (lane >> 2) * 8 + 2 * (lane & 3);
+    s_red[warp][0][e0] = w00[0]; s_red[warp][0][e0 + 1] = w00[1];
+    s_red[warp][1][e0] = m00[0]; s_red[warp][1][e0 + 1] = m00[1];
+    s_red[warp][2][e0] = w11[0]; s_red[warp][2][e0 + 1] = w11[1];
+    s_red[warp][3][e0] = m11[0]; s_red[warp][3][e0 + 1] = m11[1];
+    s_red[warp][4][e0] = w01[0]; s_red[warp][4][e0 + 1] = w01[1];
+    s_red[warp][5][e0] = p01[0]; s_red[warp][5][e0 + 1] = p01[1];
+    s_red[warp][6][e0] = q01[0]; s_red[warp][6][e0 + 1] = q01[1];
+  }
+  __syncthreads();
+  for (int i = tid; i < 7 * 64; i += JT) {
+    const int t = i >> 6, e = i & 63;
+    s_red[0][t][e] = s_red[0][t][e] + s_red[1][t][e] + s_red[2][t][e] + s_red[3][t][e];
+  }
+  __syncthreads();
+  for (int i = tid; i < 256; i += JT) {
+    const int p = i >> 4, q = i & 15;
+    const int bp = p >> 3, bq = q >> 3, r = p & 7, c = q & 7;
+    double re, im;
+    if (bp == 0 && bq == 0) { re = s_red[0][0][r * 8 + c]; im = s_red[0][1][r * 8 + c] - s_red[0][1][c * 8 + r]; }
+    else if (bp == 1 && bq == 1) { re = s_red[0][2][r * 8 + c]; im = s_red[0][3][r * 8 + c] - s_red[0][3][c * 8 + r]; }
+    else if (bp == 0) { re = s_red[0][4][r * 8 + c]; im = s_red[0][5][r * 8 + c] - s_red[0][6][r * 8 + c]; }
+    else { re = s_red[0][4][c * 8 + r]; im = -(s_red[0][5][c * 8 + r] - s_red[0][6][c * 8 + r]); }
+    sW[p * WLD + q] = make_double2(re, im);
+    sQ[p * WLD + q] = make_double2(p == q ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+  // fresh-Gram convergence test over all pairs of the 16 columns
+  {
+    int need = 0;
+    for (int i = tid; i < 256; i += JT) {
+      const int p = i >> 4, q = i & 15;
+      if (p < q) {
+        const double a = sW[p * WLD + p].x, b = sW[q * WLD + q].x;
+        const double2 g = sW[p * WLD + q];
+        if (a > dead_abs && b > dead_abs && (g.x * g.x + g.y * g.y) > tol2 * a * b) need = 1;
+      }
+    }
+    if (need) s_need = 1;   // benign race: all writers store 1
+  }
+  __syncthreads();
+  if (!s_need) return;
+  if (tid == 0) dirty[mat] = 1;
+
+  // ------------------------------------------------------------------ phase B: Jacobi sweep on W (warp 0)
+  if (warp == 0) {
+    for (int r = 0; r < 15; ++r) {
+      bool rot = false;
+      if (lane < 8) {
+        int p = (lane == 0) ? 15 : (r + lane) % 15;
+        int q = (r + 15 - lane) % 15;
+        if (p > q) { const int t = p; p = q; q = t; }
+        const double a = sW[p * WLD + p].x, b = sW[q * WLD + q].x;
+        const double2 g = sW[p * WLD + q];
+        const double g2 = g.x * g.x + g.y * g.y;
+        double c = 1.0;
+        double2 sg = make_double2(0.0, 0.0);
+        if (a > dead_abs && b > dead_abs && g2 > tol2 * a * b) {
+          rot = true;
+          const double d = b - a;
+          const double h = sqrt(d * d + 4.0 * g2);
+          const double u = (d >= 0.0 ? 2.0 : -2.0) / (fabs(d) + h);
+          c = rsqrt(1.0 + u * u * g2);
+          sg = rmul(c * u, g);   // sigma = s * gamma/|gamma|
+        }
+        s_rc[lane] = c; s_rs[lane] = sg; s_rp[lane] = p; s_rq[lane] = q;
+      }
+      const unsigned any = __ballot_sync(0xffffffffu, rot);
+      if (!any) continue;
+      __syncwarp();
+      // W <- J^H W J   (J_a = [[c, s],[-conj(s), c]] on columns (p,q) of pair a)
+#pragma unroll
+      for (int b2 = 0; b2 < 2; ++b2) {
+        const int blk = lane + 32 * b2;
+        const int ia = blk >> 3, ib = blk & 7;
+        const int pa = s_rp[ia], qa = s_rq[ia], pb = s_rp[ib], qb = s_rq[ib];
+        const double ca = s_rc[ia], cb = s_rc[ib];
+        const double2 sa = s_rs[ia], sb = s_rs[ib];
+        const double2 w00 = sW[pa * WLD + pb], w01 = sW[pa * WLD + qb], w10 = sW[qa * WLD + pb], w11 = sW[qa * WLD + qb];
+        const double2 t00 = csub(rmul(ca, w00), cmul(sa, w10));
+        const double2 t01 = csub(rmul(ca, w01), cmul(sa, w11));
+        const double2 t10 = cadd(cmulc(sa, w00), rmul(ca, w10));
+        const double2 t11 = cadd(cmulc(sa, w01), rmul(ca, w11));
+        // (t * J_b): col p = t[:,0]*cb - t[:,1]*conj(sb) ; col q = t[:,0]*sb + t[:,1]*cb
+        sW[pa * WLD + pb] = csub(rmul(cb, t00), cmulc(sb, t01));
+        sW[pa * WLD + qb] = cadd(cmul(sb, t00), rmul(cb, t01));
+        sW[qa * WLD + pb] = csub(rmul(cb, t10), cmulc(sb, t11));
+        sW[qa * WLD + qb] = cadd(cmul(sb, t10), rmul(cb, t11));
+      }
+      // Q <- Q J
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int it = lane + 32 * k;
+        const int row = it >> 3, ia = it & 7;
+        const int pa = s_rp[ia], qa = s_rq[ia];
+        const double ca = s_rc[ia];
+        const double2 sa = s_rs[ia];
+        const double2 x = sQ[row * WLD + pa], y = sQ[row * WLD + qa];
+        sQ[row * WLD + pa] = csub(rmul(ca, x), cmulc(sa, y));
+        sQ[row * WLD + qa] = cadd(cmul(sa, x), rmul(ca, y));
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase C: X <- X Q on DMMA, in place
+  {
+    double2 qf[4][2];
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4)
+#pragma unroll
+      for (int jn = 0; jn < 2; ++jn) qf[k4][jn] = sQ[(4 * k4 + (lane & 3)) * WLD + 8 * jn + (lane >> 2)];
+    const double2* src[4];
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      const int c = s_cols[4 * k4 + (lane & 3)];
+      src[k4] = (c >= 0) ? G + (size_t)ldg * c : nullptr;
+    }
+    double2* dst[2][2];
+#pragma unroll
+    for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = s_cols[8 * jn + 2 * (lane & 3) + e];
+        dst[jn][e] = (c >= 0) ? G + (size_t)ldg * c : nullptr;
+      }
+    const int nch = (M + 7) >> 3;
+    constexpr int UN = 2;
+    for (int base = warp * UN; base < nch; base += 4 * UN) {
+      double2 xa[UN][4];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int row = 8 * (base + u) + (lane >> 2);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) xa[u][k4] = (row < M && src[k4]) ? src[k4][row] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        double re[2][2] = {{0, 0}, {0, 0}}, im[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const double ar = xa[u][k4].x, ai = xa[u][k4].y, nai = -ai;
+#pragma unroll
+          for (int jn = 0; jn < 2; ++jn) {
+            dmma884(re[jn][0], re[jn][1], ar, qf[k4][jn].x);
+            dmma884(im[jn][0], im[jn][1], ar, qf[k4][jn].y);
+            dmma884(re[jn][0], re[jn][1], nai, qf[k4][jn].y);
+            dmma884(im[jn][0], im[jn][1], ai, qf[k4][jn].x);
+          }
+        }
+        const int row = 8 * (base + u) + (lane >> 2);
+        if (row < M) {
+#pragma unroll
+          for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              if (dst[jn][e]) dst[jn][e][row] = make_double2(re[jn][e], im[jn][e]);
+        }
+      }
+    }
+  }
+}
+
+// fro2[m] += ||G_m||_F^2 (slice blockIdx.x of 16); fro2 must be zeroed before the launch
+__global__ void __launch_bounds__(256) fro2_kernel(const JacobiProblem* __restrict__ probs, double* __restrict__ fro2) {
+  const JacobiProblem P = probs[blockIdx.y];
+  const size_t total = (size_t)P.M * P.N;   // ldg == M
+  double s = 0.0;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const double2 v = P.G[i];
+    s += v.x * v.x + v.y * v.y;
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && sh[0] != 0.0) atomicAdd(fro2 + blockIdx.y, sh[0]);
+}
+
+__global__ void jacobi_check_kernel(int batch, int* dirty, int* done, int* remaining) {
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  for (int m = threadIdx.x; m < batch; m += blockDim.x) {
+    if (!done[m]) {
+      if (!dirty[m]) done[m] = 1;
+      else atomicAdd(&cnt, 1);
+    }
+    dirty[m] = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *remaining = cnt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column norms -> descending order -> truncation rule -> write-back scales
+__global__ void __launch_bounds__(256) trunc_kernel(const TruncProblem* __restrict__ probs, double cutoff, int cutoff_on_sqrt,
+                                                    int max_bond, int gauge, int renorm, double null_tol) {
+  const TruncProblem P = probs[blockIdx.x];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = P.M, N = P.N;
+  for (int col = warp; col < N; col += 8) {
+    const double2* g = P.G + (size_t)P.ldg * col;
+    double s = 0.0;
+    for (int r = lane; r < M; r += 32) { const double2 v = g[r]; s += v.x * v.x + v.y * v.y; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) P.sig2[col] = s;
+  }
+  __syncthreads();
+  for (int k = tid; k < N; k += 256) {
+    const double v = P.sig2[k];
+    int rank = 0;
+    for (int j = 0; j < N; ++j) {
+      const double w = P.sig2[j];
+      rank += (w > v || (w == v && j < k)) ? 1 : 0;
+    }
+    P.perm[rank] = k;
+    P.sigma[rank] = sqrt(v);
+  }
+  __syncthreads();
+  __shared__ int s_keep;
+  __shared__ double s_rn;
+  if (tid == 0) {
+    // truncateSvdTensors, ExaTnMpsVisitor.cpp:2434-2445: first k whose partial norm is below eps, PLUS ONE
+    int cut = N;
+    for (int k = 0; k < N; ++k) {
+      const double metric = cutoff_on_sqrt ? sqrt(P.sigma[k]) : P.sigma[k];
+      if (metric < cutoff) { cut = k + 1; break; }
+    }
+    int keep = cut < max_bond ? cut : max_bond;
+    if (keep < 1) keep = 1;
+    double tot = 0.0, kept = 0.0;
+    for (int k = 0; k < N; ++k) {
+      const double s2 = P.sigma[k] * P.sigma[k];
+      tot += s2;
+      if (k < keep) kept += s2;
+    }
+    *P.keep = keep;
+    P.weights[0] = tot;
+    P.weights[1] = kept;
+    s_keep = keep;
+    s_rn = (renorm && kept > 0.0) ? sqrt(tot / kept) : 1.0;
+  }
+  __syncthreads();
+  const int keep = s_keep;
+  for (int k = tid; k < keep; k += 256) {
+    const double s = P.sigma[k];
+    double sP = 0.0, sO = 0.0;
+    // sigma_k <= null_tol * sigma_max is numerically null: without an accumulated V its right vector is noise amplified by
+    // tol * sigma_max / sigma_k, so both factors of that component are dropped (contribution to theta <= null_tol * sigma_max)
+    if (s > 1e-100 && s > null_tol * P.sigma[0]) {
+      // lo site carries sigma^el, hi site sigma^eh
+      const double lo_f = (gauge == 0) ? sqrt(s) : (gauge == 1 ? 1.0 : s);
+      const double hi_f = ((gauge == 0) ? sqrt(s) : (gauge == 1 ? s : 1.0)) * s_rn;
+      if (P.tall) { sP = lo_f / s; sO = hi_f / (s * s); }
+      else { sP = hi_f / s; sO = lo_f / (s * s); }
+    }
+    P.scaleP[k] = sP;
+    P.scaleO[k] = sO;
+  }
+}
+
+__global__ void gather_kernel(const GatherProblem* __restrict__ probs) {
+  const GatherProblem P = probs[blockIdx.z];
+  const int k = blockIdx.y;
+  if (k >= P.keep) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.M) return;
+  const double sc = P.scale[k];
+  const double2 v = P.G[(size_t)i + (size_t)P.ldg * P.perm[k]];
+  if (P.conjT) P.out[(size_t)k + (size_t)P.ldo * i] = make_double2(sc * v.x, -sc * v.y);
+  else P.out[(size_t)i + (size_t)P.ldo * k] = make_double2(sc * v.x, sc * v.y);
+}
+
+}  // namespace
+
+void launch_jacobi_step(const JacobiProblem* d_probs, int batch, int max_pairs, int step, double tol2, double dead2,
+                        const double* d_fro2, int* d_dirty, const int* d_done, cudaStream_t s) {
+  if (batch <= 0) return;
+  dim3 grid(max_pairs, batch);
+  jacobi_step_kernel<<<grid, JT, 0, s>>>(d_probs, step, tol2, dead2, d_fro2, d_dirty, d_done);
+}
+void launch_fro2(const JacobiProblem* d_probs, int batch, double* d_fro2, cudaStream_t s) {
+  if (batch <= 0) return;
+  dim3 grid(16, batch);
+  fro2_kernel<<<grid, 256, 0, s>>>(d_probs, d_fro2);
+}
+void launch_jacobi_check(int batch, int* d_dirty, int* d_done, int* d_remaining, cudaStream_t s) {
+  jacobi_check_kernel<<<1, 256, 0, s>>>(batch, d_dirty, d_done, d_remaining);
+}
+void launch_trunc(const TruncProblem* d_probs, int batch, double cutoff, int cutoff_on_sqrt, int max_bond, int gauge, int renorm,
+                  double null_tol, cudaStream_t s) {
+  if (batch <= 0) return;
+  trunc_kernel<<<batch, 256, 0, s>>>(d_probs, cutoff, cutoff_on_sqrt, max_bond, gauge, renorm, null_tol);
+}
+void launch_gather(const GatherProblem* d_probs, int batch, int max_rows, int max_keep, cudaStream_t s) {
+  if (batch <= 0 || max_rows <= 0 || max_keep <= 0) return;
+  dim3 grid((max_rows + 255) / 256, max_keep, batch);
+  gather_kernel<<<grid, 256, 0, s>>>(d_probs);
+}
+
+}  // namespace mpsb200
