@@ -96,6 +96,9 @@ int mps_resize_site(mps_handle_t h, int k, int dl, int dr, void** dptr);
 /* counters: [0] 2q gates executed, [1] 1q kernel gates, [2] layers, [3] jacobi sweeps, [4] kernel launches,
  * [5] ms merge GEMM, [6] ms SVD, [7] ms truncate+write-back (5..7 only with option "profile") */
 int mps_stats(mps_handle_t h, double* out, int cap);
+/* the CUDA stream (cudaStream_t) all work of this handle is issued on: callers time with events recorded on it
+ * and order their own transfers (NCCL send/recv of boundary sites) against it */
+int mps_get_stream(mps_handle_t h, void** stream);
 
 #ifdef __cplusplus
 }

@@ -124,11 +124,16 @@ def test_truncated_parity_within_reference_spread(O, n, depth, chi):
     zo = np.array([o.expval_z([k]) for k in range(n)])
     assert np.abs(e.expval_z_all() - zo).max() < TRUNC_TOL
     assert abs(e.norm() - o.norm()) < TRUNC_TOL
-    assert list(e.bond_dims()) == list(o.bond_dims())
-    # retained singular values of the last SVD on a saturated bond
-    b = n // 2
-    s_g, s_o = e.singular_values(b), o.singular_values(b)
-    assert len(s_g) == len(s_o) and np.abs(s_g - s_o).max() < TRUNC_TOL
+    # With the default svd-cutoff (DBL_MIN) the reference rule (ExaTnMpsVisitor.cpp:2434-2443) drops a bond slice only
+    # when its partial norm is an exact floating-point zero, so on rank-deficient thetas the kept dimension depends on
+    # whether the SVD driver returns 0.0 or 1e-17 noise (zgesvd and zgesdd already disagree).  The slices in question carry
+    # no weight: bond dimensions must agree wherever the singular values are above noise.
+    for k, (bg, bo) in enumerate(zip(e.bond_dims(), o.bond_dims())):
+        s_g, s_o = e.singular_values(k), o.singular_values(k)
+        m = min(len(s_g), len(s_o))
+        assert bg <= chi and bo <= chi
+        assert np.abs(s_g[:m] - s_o[:m]).max() < TRUNC_TOL, k
+        assert (s_g[m:] < 1e-12).all() and (s_o[m:] < 1e-12).all(), k
     assert abs(e.discarded_weight() - o.discarded_weight()) < 1e-4 * max(1.0, o.discarded_weight())
     e.close()
 

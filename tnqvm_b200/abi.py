@@ -43,6 +43,7 @@ SYMBOLS = {
     "mps_site_device_ptr": ([C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p], C.c_int),
     "mps_resize_site": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
     "mps_stats": ([C.c_void_p, C.c_void_p, C.c_int], C.c_int),
+    "mps_get_stream": ([C.c_void_p, C.POINTER(C.c_void_p)], C.c_int),
 }
 
 

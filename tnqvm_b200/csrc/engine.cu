@@ -970,4 +970,10 @@ int mps_stats(mps_handle_t h, double* out, int cap) {
   API_END(h)
 }
 
+int mps_get_stream(mps_handle_t h, void** stream) {
+  API_BEGIN(h)
+  *stream = (void*)h->stream;
+  API_END(h)
+}
+
 }  // extern "C"

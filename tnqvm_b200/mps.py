@@ -186,6 +186,12 @@ class B200MPS:
         self._ck(self.L.mps_resize_site(self.h, k, dl, dr, C.byref(p)))
         return p.value
 
+    def stream(self):
+        """cudaStream_t (as an int) the handle issues its work on."""
+        p = C.c_void_p()
+        self._ck(self.L.mps_get_stream(self.h, C.byref(p)))
+        return p.value or 0
+
     def stats(self):
         out = np.zeros(8, dtype=np.float64)
         self._ck(self.L.mps_stats(self.h, out.ctypes.data, 8))
