@@ -1,0 +1,94 @@
+"""The C++ host side above the C ABI: tnqvm::B200MpsVisitor driven like TNQVM::execute (tnqvm/TNQVM.cpp:106-139) by
+b200_tnqvm_run.  CPU part: XASM reader + nearest-neighbour pass.  GPU part: the reference gtests' known answers
+(tnqvm/visitors/exatn-mps/tests/MpsGateTester.cpp, MpsMeasurementTester.cpp, NumericalTesterCheckNorm.cpp) through
+the visitor's own AcceleratorBuffer outputs ("norm", "exp-val-z", bit-string counts)."""
+import json
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import reference_cases as RC
+from tnqvm_b200 import circuits as Cc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RUN = os.path.join(ROOT, "tnqvm_b200", "lib", "b200_tnqvm_run")
+
+
+def run(circ, n, *args):
+    p = subprocess.run([RUN, "--xasm", "-", "--qubits", str(n)] + [str(a) for a in args], input=Cc.to_xasm(circ), capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    return p.stdout
+
+
+def test_driver_is_built_and_links_the_cuda_library():
+    assert os.path.exists(RUN)
+    out = subprocess.run(["ldd", RUN], capture_output=True, text=True).stdout
+    assert "libmps_b200.so" in out and "libtnqvm_b200_visitor.so" in out
+
+
+def test_cpp_nearest_neighbor_pass_matches_host_restatement():
+    # NearestNeighborTransform.hpp:43-135 restated twice (C++ pre-pass and tnqvm_b200.circuits): they must agree
+    rng = np.random.default_rng(5)
+    circ = []
+    for _ in range(40):
+        a, b = rng.choice(12, 2, replace=False)
+        circ.append([("CNOT", (int(a), int(b)), ()), ("fSim", (int(a), int(b)), (0.3, -0.2)), ("Rz", (int(a),), (1.25,))][int(rng.integers(0, 3))])
+    out = run(circ, 12, "--dump-nn").strip().splitlines()
+    ref = Cc.nearest_neighbor(circ)
+    assert len(out) == len(ref)
+    for line, g in zip(out, ref):
+        tok = line.split()
+        assert tok[0] == g[0] and tuple(int(t) for t in tok[1:1 + len(g[1])]) == tuple(g[1])
+        assert np.allclose([float(t) for t in tok[1 + len(g[1]):]], list(g[2]))
+    syc = "/root/reference/examples/sycamore/resources/sycamore_53_14_0.xasm"
+    if os.path.exists(syc):   # build container only
+        p = subprocess.run([RUN, "--xasm", syc, "--dump-nn"], capture_output=True, text=True)
+        lines = p.stdout.strip().splitlines()
+        assert sum(1 for l in lines if len(l.split()) >= 3 and l.split()[0] in ("Swap", "fSim")) == 1897
+
+
+def test_no_gpu_no_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p = subprocess.run([RUN, "--xasm", "-", "--qubits", "2"], input="H(q[0]);\n", capture_output=True, text=True)
+    assert p.returncode != 0 and "no CUDA device" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", RC.PROB_CASES, ids=[c["name"] for c in RC.PROB_CASES])
+def test_visitor_reference_gtests_sampled(case):
+    # shots >= 1 -> appendMeasurement strings; the gtests assert probabilities within 0.05 / 0.01 / 0.1 on 10 000 shots
+    res = json.loads(run(case["circuit"], case["n"], "--shots", 10000, "--seed", 123))
+    tot = sum(res["counts"].values())
+    assert tot == 10000
+    for s, p in case["expect"].items():
+        assert abs(res["counts"].get(s, 0) / tot - p) < 0.03, (case["cite"], res["counts"])
+    assert abs(res["norm"] - 1.0) < 1e-12
+
+
+@pytest.mark.gpu
+def test_visitor_expval_z_deuteron_and_seed_determinism():
+    for t, ref in zip(RC.deuteron_angles(), RC.DEUTERON_TABLE):
+        res = json.loads(run(RC.deuteron_circuit(t), 2))     # shots < 1 -> "exp-val-z"  (MpsGateTester.cpp:359-407)
+        assert abs(res["exp-val-z"] - ref) < 2e-6
+    a = json.loads(run(RC.ghz4_measured(), 4, "--shots", 8192, "--seed", 123))["counts"]
+    for _ in range(3):                                        # MpsMeasurementTester.cpp:37-66
+        assert json.loads(run(RC.ghz4_measured(), 4, "--shots", 8192, "--seed", 123))["counts"] == a
+    assert set(a) == {"0000", "1111"}
+
+
+@pytest.mark.gpu
+def test_visitor_large_register_sampling_and_norm():
+    res = json.loads(run(RC.ghz35(), 35, "--shots", 20, "--seed", 9))   # MpsMeasurementTester.cpp:7-35
+    assert set(res["counts"]) <= {"0000", "1111"} and sum(res["counts"].values()) == 20
+    circ = [g for g in Cc.rcs(10, 15, seed=4)]
+    for extra in ([], ["--svd-cutoff", 1e-16]):                          # NumericalTesterCheckNorm.cpp:15-62
+        res = json.loads(run(circ, 10, "--shots", 8, *extra))
+        assert abs(res["norm"] - 1.0) < 1e-6
+    # amplitude output (computeWaveFuncSlice with a closed bit string, ExaTnMpsVisitor.cpp:2588-2675): GHZ 1/sqrt(2)
+    res = json.loads(run([g for g in RC.ghz4_measured() if g[0] != "Measure"], 4, "--bitstring", "1111"))
+    assert abs(res["amplitude"][0] - math.sqrt(0.5)) < 1e-12 and abs(res["amplitude"][1]) < 1e-12

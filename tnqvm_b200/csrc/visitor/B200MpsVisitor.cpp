@@ -1,0 +1,199 @@
+// See B200MpsVisitor.hpp.  Reference behaviour followed line by line (nothing copied):
+//   initialize  ExaTnMpsVisitor.cpp:173-346   options, reset to |0...0>
+//   visit(*)    ExaTnMpsVisitor.cpp:870-1085  gate -> applyGate; Swap pre-sorts its bits (:1030-1033); Measure records (:991-994)
+//   finalize    ExaTnMpsVisitor.cpp:576-670   "norm", "exp-val-z" (shots < 1) or bit strings (shots >= 1)
+#include "B200MpsVisitor.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+namespace tnqvm {
+
+int b200GateMatrix(const std::string& name, const std::vector<double>& p, std::complex<double> m[16]) {
+  typedef std::complex<double> C;
+  const C I(0.0, 1.0);
+  auto P = [&](size_t i) { return i < p.size() ? p[i] : 0.0; };
+  auto set2 = [&](C a, C b, C c, C d) { m[0] = a; m[1] = b; m[2] = c; m[3] = d; return 2; };
+  auto ctrl = [&](C a, C b, C c, C d) {   // controlled-U on (q0 = control, q1 = target), index 2*b0 + b1
+    for (int i = 0; i < 16; ++i) m[i] = 0.0;
+    m[0] = m[5] = 1.0;
+    m[10] = a; m[11] = b; m[14] = c; m[15] = d;
+    return 4;
+  };
+  const double s2 = std::sqrt(0.5);
+  if (name == "H") return set2(s2, s2, s2, -s2);
+  if (name == "X") return set2(0, 1, 1, 0);
+  if (name == "Y") return set2(0, -I, I, 0);
+  if (name == "Z") return set2(1, 0, 0, -1);
+  if (name == "T") return set2(1, 0, 0, std::exp(I * (M_PI / 4)));
+  if (name == "Tdg") return set2(1, 0, 0, std::exp(-I * (M_PI / 4)));
+  if (name == "S") return set2(1, 0, 0, I);
+  if (name == "Sdg") return set2(1, 0, 0, -I);
+  if (name == "Rx") { const double c = std::cos(P(0) / 2), s = std::sin(P(0) / 2); return set2(c, -I * s, -I * s, c); }
+  if (name == "Ry") { const double c = std::cos(P(0) / 2), s = std::sin(P(0) / 2); return set2(c, -s, s, c); }
+  if (name == "Rz") return set2(std::exp(-I * (P(0) / 2)), 0, 0, std::exp(I * (P(0) / 2)));
+  if (name == "U" || name == "U3") {
+    const double c = std::cos(P(0) / 2), s = std::sin(P(0) / 2);
+    return set2(c, -std::exp(I * P(2)) * s, std::exp(I * P(1)) * s, std::exp(I * (P(1) + P(2))) * c);
+  }
+  if (name == "CNOT" || name == "CX") return ctrl(0, 1, 1, 0);
+  if (name == "CZ") return ctrl(1, 0, 0, -1);
+  if (name == "CY") return ctrl(0, -I, I, 0);
+  if (name == "CH") return ctrl(s2, s2, s2, -s2);
+  if (name == "CRZ") return ctrl(std::exp(-I * (P(0) / 2)), 0, 0, std::exp(I * (P(0) / 2)));
+  if (name == "CPhase") return ctrl(1, 0, 0, std::exp(I * P(0)));
+  if (name == "Swap" || name == "iSwap" || name == "fSim") {
+    for (int i = 0; i < 16; ++i) m[i] = 0.0;
+    m[0] = 1.0;
+    if (name == "Swap") { m[6] = m[9] = 1.0; m[15] = 1.0; }
+    else if (name == "iSwap") { m[6] = m[9] = I; m[15] = 1.0; }
+    else {
+      const double c = std::cos(P(0)), s = std::sin(P(0));
+      m[5] = m[10] = c; m[6] = m[9] = -I * s; m[15] = std::exp(-I * P(1));
+    }
+    return 4;
+  }
+  return set2(1, 0, 0, 1);   // unknown name: identity (ExatnUtils.cpp:112)
+}
+
+B200MpsVisitor::B200MpsVisitor() {}
+
+B200MpsVisitor::~B200MpsVisitor() {
+  if (m_handle) mps_destroy(m_handle);
+}
+
+void B200MpsVisitor::check(int rc, const char* what) const {
+  if (rc != 0) {
+    const char* msg = mps_last_error(m_handle);
+    xacc::error(std::string("B200MpsVisitor: ") + what + " failed: " + (msg ? msg : "?"));
+  }
+}
+
+void B200MpsVisitor::initialize(std::shared_ptr<AcceleratorBuffer> in_buffer, int nbShots) {
+  double svdCutoff = -1.0;   // -> DBL_MIN inside the engine (ExaTnMpsVisitor.cpp:257)
+  if (options.keyExists<double>("svd-cutoff")) svdCutoff = options.get<double>("svd-cutoff");
+  int maxBondDim = 0;        // -> unlimited (ExaTnMpsVisitor.cpp:265)
+  if (options.keyExists<int>("max-bond-dim")) maxBondDim = options.get<int>("max-bond-dim");
+  int device = 0, gauge = MPS_GAUGE_REFERENCE;
+  if (options.keyExists<int>("b200-device")) device = options.get<int>("b200-device");
+  if (options.keyExists<int>("b200-gauge")) gauge = options.get<int>("b200-gauge");
+  uint64_t seed = 0;
+  if (options.keyExists<int>("seed")) seed = (uint64_t)options.get<int>("seed");   // TNQVM.hpp:114-117
+
+  m_buffer = std::move(in_buffer);
+  buffer = m_buffer;
+  m_measureQubits.clear();
+  m_shotCount = nbShots;
+  const int n = m_buffer->size();
+  // the registered service instance is reused across execute() calls (TNQVM.cpp:109): a fresh state every time
+  if (m_handle) { mps_destroy(m_handle); m_handle = nullptr; }
+  m_nQubits = n;
+  const int rc = mps_create(n, 1, maxBondDim, svdCutoff, gauge, device, seed, &m_handle);
+  if (rc != 0) {
+    const char* msg = mps_last_error(nullptr);
+    xacc::error(std::string("B200MpsVisitor: cannot create the MPS engine: ") + (msg ? msg : "?"));
+  }
+  if (options.keyExists<bool>("b200-cutoff-on-sqrt") && options.get<bool>("b200-cutoff-on-sqrt"))
+    check(mps_set_option(m_handle, "cutoff_on_sqrt", 1.0), "set_option");
+}
+
+void B200MpsVisitor::applyGate(xacc::Instruction& inst) {
+  std::vector<double> params;
+  for (int i = 0; i < (int)inst.getParameters().size(); ++i) params.push_back(inst.getParameter(i).as<double>());
+  std::complex<double> m[16];
+  const int dim = b200GateMatrix(inst.name(), params, m);
+  const auto bits = inst.bits();
+  if (dim == 2) {
+    check(mps_apply_1q(m_handle, (int)bits[0], reinterpret_cast<const double*>(m)), "apply_1q");
+  } else {
+    if (bits.size() != 2) xacc::error("two-qubit gate with " + std::to_string(bits.size()) + " bits");
+    check(mps_apply_2q(m_handle, (int)bits[0], (int)bits[1], reinterpret_cast<const double*>(m)), "apply_2q");
+  }
+}
+
+void B200MpsVisitor::visit(Swap& g) {
+  // ExaTnMpsVisitor.cpp:1030-1033: bits sorted descending before the gate tensor is applied (Swap is symmetric)
+  auto b = g.bits();
+  if (b.size() == 2 && b[0] < b[1]) g.setBits({b[1], b[0]});
+  applyGate(g);
+}
+
+void B200MpsVisitor::visit(Measure& g) {
+  m_measureQubits.push_back(g.bits()[0]);
+  check(mps_measure(m_handle, (int)g.bits()[0]), "measure");
+}
+
+void B200MpsVisitor::finalize() {
+  if (!m_handle) xacc::error("B200MpsVisitor::finalize called before initialize");
+  double norm = 0.0;
+  check(mps_norm(m_handle, 0, &norm), "norm");
+  m_buffer->addExtraInfo("norm", norm);   // reference adds it for n < 20 only (:612); harmless beyond
+  if (!m_measureQubits.empty()) {
+    if (m_shotCount < 1 && m_nQubits < 20) {
+      // "exp-val-z": raw <psi| prod Z |psi>, not divided by the norm (:616-644)
+      std::vector<int> q(m_measureQubits.begin(), m_measureQubits.end());
+      double ez = 0.0;
+      check(mps_expval_z(m_handle, 0, (int)q.size(), q.data(), &ez), "expval_z");
+      m_buffer->addExtraInfo("exp-val-z", ez);
+    } else if (m_shotCount >= 1) {
+      const int nm = (int)m_measureQubits.size();
+      std::vector<char> out((size_t)m_shotCount * nm + 1);
+      int produced = 0;
+      check(mps_sample(m_handle, 0, m_shotCount, out.data(), &produced), "sample");
+      for (int s = 0; s < produced; ++s) m_buffer->appendMeasurement(std::string(out.data() + (size_t)s * nm, nm));
+    }
+  }
+  std::vector<double> st = engineStats();
+  executionInfo.insert("b200-gates-2q", st[0]);
+  executionInfo.insert("b200-kernel-launches", st[4]);
+  executionInfo.insert("b200-discarded-weight", discardedWeight());
+}
+
+const double B200MpsVisitor::getExpectationValueZ(std::shared_ptr<CompositeInstruction> function) {
+  // ExaTnMpsVisitor.cpp:1087-1117 walks the circuit and then estimates <Z...Z> from 100000 samples; here the same
+  // quantity is computed exactly by one transfer-matrix sweep.
+  InstructionIterator it(function);
+  while (it.hasNext()) {
+    auto inst = it.next();
+    if (inst->isEnabled()) inst->accept(this);
+  }
+  if (m_measureQubits.empty()) return 0.0;
+  std::vector<int> q(m_measureQubits.begin(), m_measureQubits.end());
+  double ez = 0.0, nrm = 1.0;
+  check(mps_expval_z(m_handle, 0, (int)q.size(), q.data(), &ez), "expval_z");
+  check(mps_norm(m_handle, 0, &nrm), "norm");
+  return nrm > 0 ? ez / nrm : 0.0;   // the sampled estimate of the reference is implicitly normalised
+}
+
+const std::vector<std::complex<double>> B200MpsVisitor::getState() {
+  if (!m_handle || m_nQubits > 30) return {};
+  std::vector<std::complex<double>> sv((size_t)1 << m_nQubits);
+  check(mps_statevector(m_handle, 0, reinterpret_cast<double*>(sv.data())), "statevector");
+  return sv;
+}
+
+std::vector<double> B200MpsVisitor::engineStats() const {
+  std::vector<double> st(8, 0.0);
+  if (m_handle) check(mps_stats(m_handle, st.data(), 8), "stats");
+  return st;
+}
+std::vector<int> B200MpsVisitor::bondDimensions() const {
+  std::vector<int> b(std::max(m_nQubits - 1, 1), 1);
+  if (m_handle) check(mps_bond_dims(m_handle, b.data()), "bond_dims");
+  b.resize(std::max(m_nQubits - 1, 0));
+  return b;
+}
+double B200MpsVisitor::discardedWeight() const {
+  double w = 0.0;
+  if (m_handle) check(mps_discarded_weight(m_handle, &w), "discarded_weight");
+  return w;
+}
+std::complex<double> B200MpsVisitor::amplitude(const std::vector<int>& bits) const {
+  std::vector<int8_t> b(bits.begin(), bits.end());
+  std::complex<double> out(0, 0);
+  size_t len = 0;
+  for (auto v : b) if (v < 0) xacc::error("amplitude(): open legs are not supported through this accessor");
+  check(mps_amplitude(m_handle, 0, b.data(), reinterpret_cast<double*>(&out), &len), "amplitude");
+  return out;
+}
+}  // namespace tnqvm

@@ -1,0 +1,221 @@
+// b200_tnqvm_run -- drives tnqvm::B200MpsVisitor exactly the way the accelerator does (reference: TNQVM::execute,
+// tnqvm/TNQVM.cpp:106-139): setOptions -> initialize(buffer, shots) -> nearest-neighbour rewrite (max-distance 1)
+// -> accept(visitor) for every enabled instruction -> finalize -> results in the AcceleratorBuffer.
+// It stands in for the XACC runtime, which is not installed here: circuits come from the XASM subset the reference's
+// tests and examples/sycamore/resources/*.xasm use.  Output: one JSON object on stdout.
+//
+// The nearest-neighbour pass restates the meet-in-the-middle Swap ladder of "lnn-transform"
+// (tnqvm/visitors/exatn-mps/NearestNeighborTransform.hpp:43-135); the accelerator itself calls XACC's external "nnizer".
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "B200MpsVisitor.hpp"
+
+namespace xacc {
+std::shared_ptr<Instruction> createInstruction(const std::string& nm, const std::vector<std::size_t>& bits,
+                                               const std::vector<InstructionParameter>& params) {
+  using namespace xacc::quantum;
+#define MK(N, CLS) if (nm == N) return std::make_shared<CLS>(bits, params);
+  MK("I", Identity) MK("H", Hadamard) MK("X", X) MK("Y", Y) MK("Z", Z) MK("Rx", Rx) MK("Ry", Ry) MK("Rz", Rz) MK("T", T)
+  MK("Tdg", Tdg) MK("S", S) MK("Sdg", Sdg) MK("U", U) MK("U3", U) MK("CPhase", CPhase) MK("CNOT", CNOT) MK("CX", CNOT)
+  MK("Swap", Swap) MK("CZ", CZ) MK("CY", CY) MK("CH", CH) MK("CRZ", CRZ) MK("iSwap", iSwap) MK("fSim", fSim)
+  MK("Measure", Measure)
+#undef MK
+  xacc::error("unknown instruction: " + nm);
+}
+}  // namespace xacc
+
+namespace {
+using namespace xacc;
+
+// tiny arithmetic evaluator for XASM parameters: numbers, pi, + - * /, parentheses, unary minus
+struct Expr {
+  const char* p;
+  double num() {
+    while (isspace(*p)) ++p;
+    if (*p == '(') { ++p; double v = sum(); while (isspace(*p)) ++p; if (*p == ')') ++p; return v; }
+    if (*p == '-') { ++p; return -num(); }
+    if (*p == '+') { ++p; return num(); }
+    if (!strncmp(p, "pi", 2)) { p += 2; return M_PI; }
+    char* e; double v = strtod(p, &e);
+    if (e == p) xacc::error(std::string("cannot parse parameter near: ") + p);
+    p = e; return v;
+  }
+  double prod() { double v = num(); for (;;) { while (isspace(*p)) ++p; if (*p == '*') { ++p; v *= num(); } else if (*p == '/') { ++p; v /= num(); } else return v; } }
+  double sum() { double v = prod(); for (;;) { while (isspace(*p)) ++p; if (*p == '+') { ++p; v += prod(); } else if (*p == '-') { ++p; v -= prod(); } else return v; } }
+};
+
+std::shared_ptr<CompositeInstruction> parseXasm(const std::string& text, int& nQubitsSeen) {
+  auto kernel = std::make_shared<CompositeInstruction>("kernel");
+  std::istringstream in(text);
+  std::string line;
+  nQubitsSeen = 0;
+  while (std::getline(in, line)) {
+    const auto c = line.find("//");
+    if (c != std::string::npos) line = line.substr(0, c);
+    const auto lp = line.find('('), rp = line.rfind(')');
+    if (lp == std::string::npos || rp == std::string::npos || line.find("__qpu__") != std::string::npos) continue;
+    std::string name = line.substr(0, lp);
+    name.erase(0, name.find_first_not_of(" \t"));
+    name.erase(name.find_last_not_of(" \t") + 1);
+    if (name.empty()) continue;
+    std::vector<std::size_t> bits;
+    std::vector<InstructionParameter> params;
+    std::string args = line.substr(lp + 1, rp - lp - 1), a;
+    int depth = 0;
+    std::vector<std::string> parts;
+    for (char ch : args) {
+      if (ch == '(') ++depth;
+      if (ch == ')') --depth;
+      if (ch == ',' && depth == 0) { parts.push_back(a); a.clear(); } else a += ch;
+    }
+    if (!a.empty()) parts.push_back(a);
+    for (auto& s : parts) {
+      const auto lb = s.find('['), rb = s.find(']');
+      const auto first = s.find_first_not_of(" \t");
+      if (lb != std::string::npos && rb != std::string::npos && first != std::string::npos && (isalpha(s[first]) || s[first] == '_') &&
+          s.substr(first, 2) != "pi") {
+        bits.push_back((std::size_t)atoi(s.substr(lb + 1, rb - lb - 1).c_str()));
+      } else if (first != std::string::npos) {
+        Expr e{s.c_str()};
+        params.emplace_back(e.sum());
+      }
+    }
+    for (auto b : bits) nQubitsSeen = std::max(nQubitsSeen, (int)b + 1);
+    kernel->addInstruction(createInstruction(name, bits, params));
+  }
+  return kernel;
+}
+
+void nearestNeighborTransform(std::shared_ptr<CompositeInstruction> program, int maxDistance = 1) {
+  std::vector<std::shared_ptr<Instruction>> out;
+  auto far = [&](long a, long b) { return std::labs(a - b) > maxDistance; };
+  for (auto& inst : program->getInstructions()) {
+    const auto bits = inst->bits();
+    if (bits.size() == 2 && far((long)bits[0], (long)bits[1])) {
+      const std::size_t lo0 = std::min(bits[0], bits[1]), hi0 = std::max(bits[0], bits[1]);
+      std::size_t lo = lo0, hi = hi0;
+      for (;;) {
+        out.push_back(createInstruction("Swap", {lo, lo + 1}));
+        ++lo;
+        if (!far((long)lo, (long)hi)) break;
+        out.push_back(createInstruction("Swap", {hi, hi - 1}));
+        --hi;
+        if (!far((long)lo, (long)hi)) break;
+      }
+      inst->setBits(bits[0] < bits[1] ? std::vector<std::size_t>{lo, hi} : std::vector<std::size_t>{hi, lo});
+      out.push_back(inst);
+      for (std::size_t i = lo; i > lo0; --i) out.push_back(createInstruction("Swap", {i, i - 1}));
+      for (std::size_t i = hi; i < hi0; ++i) out.push_back(createInstruction("Swap", {i, i + 1}));
+    } else {
+      out.push_back(inst);
+    }
+  }
+  program->clear();
+  program->addInstructions(out);
+}
+
+// TNQVM::execute, tnqvm/TNQVM.cpp:106-139
+void execute(std::shared_ptr<tnqvm::TNQVMVisitor> visitor, const HeterogeneousMap& options, std::shared_ptr<AcceleratorBuffer> buffer,
+             std::shared_ptr<CompositeInstruction> kernel, int shots) {
+  visitor->setOptions(options);
+  visitor->initialize(buffer, shots);
+  visitor->setKernelName(kernel->name());
+  if (visitor->name() == "exatn-mps") nearestNeighborTransform(kernel, 1);
+  InstructionIterator it(kernel);
+  while (it.hasNext()) {
+    auto inst = it.next();
+    if (inst->isEnabled()) inst->accept(visitor);
+  }
+  visitor->finalize();
+}
+}  // namespace
+
+int main(int argc, char** argv) {
+  std::string file;
+  int nq = 0, shots = -1, maxBond = 0, seed = -1, device = 0, gauge = 0;
+  double cutoff = -1.0;
+  bool wantState = false, dumpNN = false;
+  std::string bitstring;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    auto next = [&]() { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return std::string(argv[++i]); };
+    if (a == "--xasm") file = next();
+    else if (a == "--qubits") nq = atoi(next().c_str());
+    else if (a == "--shots") shots = atoi(next().c_str());
+    else if (a == "--max-bond-dim") maxBond = atoi(next().c_str());
+    else if (a == "--svd-cutoff") cutoff = atof(next().c_str());
+    else if (a == "--seed") seed = atoi(next().c_str());
+    else if (a == "--device") device = atoi(next().c_str());
+    else if (a == "--gauge") gauge = atoi(next().c_str());
+    else if (a == "--state") wantState = true;
+    else if (a == "--dump-nn") dumpNN = true;   // print the nearest-neighbourised program and exit (no GPU needed)
+    else if (a == "--bitstring") bitstring = next();
+    else { fprintf(stderr, "usage: b200_tnqvm_run --xasm FILE|- [--qubits N] [--shots S] [--max-bond-dim D] [--svd-cutoff E] [--seed K] [--state] [--bitstring 0101..]\n"); return 2; }
+  }
+  try {
+    std::stringstream ss;
+    if (file == "-" || file.empty()) ss << std::cin.rdbuf();
+    else { std::ifstream f(file); if (!f) xacc::error("cannot open " + file); ss << f.rdbuf(); }
+    int seen = 0;
+    auto kernel = parseXasm(ss.str(), seen);
+    if (nq <= 0) nq = seen;
+    if (dumpNN) {
+      nearestNeighborTransform(kernel, 1);
+      for (auto& inst : kernel->getInstructions()) {
+        printf("%s", inst->name().c_str());
+        for (auto b : inst->bits()) printf(" %zu", b);
+        for (auto& p : inst->getParameters()) printf(" %.17g", p.as<double>());
+        printf("\n");
+      }
+      return 0;
+    }
+    if (shots >= 0 && shots < 1) xacc::error("Invalid 'shots' parameter.");   // TNQVM.hpp:104-107
+    HeterogeneousMap opts;
+    opts.insert("tnqvm-visitor", std::string("exatn-mps"));
+    if (maxBond > 0) opts.insert("max-bond-dim", maxBond);
+    if (cutoff >= 0) opts.insert("svd-cutoff", cutoff);
+    if (seed >= 0) opts.insert("seed", seed);
+    opts.insert("b200-device", device);
+    opts.insert("b200-gauge", gauge);
+    auto visitor = std::make_shared<tnqvm::B200MpsVisitor>();
+    auto buffer = std::make_shared<AcceleratorBuffer>("q", nq);
+    const int nInst = kernel->nInstructions();
+    execute(visitor, opts, buffer, kernel, shots);
+    printf("{\"visitor\": \"%s\", \"qubits\": %d, \"instructions\": %d, \"instructions_after_nn\": %d", visitor->name().c_str(), nq, nInst,
+           kernel->nInstructions());
+    for (auto& kv : buffer->getInformation())
+      if (std::holds_alternative<double>(kv.second)) printf(", \"%s\": %.17g", kv.first.c_str(), std::get<double>(kv.second));
+    printf(", \"counts\": {");
+    bool first = true;
+    for (auto& kv : buffer->getMeasurementCounts()) { printf("%s\"%s\": %d", first ? "" : ", ", kv.first.c_str(), kv.second); first = false; }
+    printf("}, \"bond_dims\": [");
+    auto bd = visitor->bondDimensions();
+    for (size_t i = 0; i < bd.size(); ++i) printf("%s%d", i ? ", " : "", bd[i]);
+    printf("], \"discarded_weight\": %.17g", visitor->discardedWeight());
+    if (!bitstring.empty()) {
+      std::vector<int> bits;
+      for (char c : bitstring) bits.push_back(c == '1');
+      const auto amp = visitor->amplitude(bits);
+      printf(", \"amplitude\": [%.17g, %.17g]", amp.real(), amp.imag());
+    }
+    if (wantState) {
+      auto sv = visitor->getState();
+      printf(", \"state\": [");
+      for (size_t i = 0; i < sv.size(); ++i) printf("%s[%.17g, %.17g]", i ? ", " : "", sv[i].real(), sv[i].imag());
+      printf("]");
+    }
+    auto st = visitor->engineStats();
+    printf(", \"stats\": {\"gates_2q\": %.0f, \"layers\": %.0f, \"jacobi_sweeps\": %.0f, \"launches\": %.0f}}\n", st[0], st[2], st[3], st[4]);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "b200_tnqvm_run: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}
