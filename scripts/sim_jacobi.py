@@ -1,0 +1,156 @@
+"""CPU emulation of block one-sided Jacobi variants to study outer-sweep counts on realistic thetas (dev tool)."""
+import sys, os, math
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import oracle as O
+from tnqvm_b200 import circuits as Cc
+from tnqvm_b200.gates import gate_matrix
+
+def thetas(n=14, depth=16, chi=32, seed=3, gauge=0):
+    """Collect thetas (after gate) seen at saturated bonds."""
+    o = O.OracleMPS(n, max_bond=chi, gauge=gauge)
+    circ = Cc.brickwork(n, depth, seed=seed)
+    out = []
+    for g in circ:
+        if len(g[1]) == 2:
+            lo = min(g[1])
+            A, B = o.get_site(lo), o.get_site(lo + 1)
+            if A.shape[0] == chi and A.shape[2] == chi and B.shape[2] == chi:
+                m = gate_matrix(g[0], g[2]).reshape(2, 2, 2, 2)
+                if g[1][0] > g[1][1]:
+                    m = m.transpose(1, 0, 3, 2)
+                th = np.einsum('pqij,aijc->apqc', m, np.einsum('aik,kjc->aijc', A, B))
+                out.append(th.reshape(2 * chi, 2 * chi, order='F'))
+        o.apply(g[0], g[1], g[2])
+    return out
+
+def jacobi_eig_sweeps(W, tol, max_sweeps, dead):
+    """two-sided cyclic Jacobi on Hermitian W; returns Q, nrot"""
+    n = W.shape[0]
+    W = W.copy(); Q = np.eye(n, dtype=complex); nrot = 0
+    for s in range(max_sweeps):
+        rot = 0
+        for p in range(n - 1):
+            for q in range(p + 1, n):
+                a, b, g = W[p, p].real, W[q, q].real, W[p, q]
+                g2 = abs(g) ** 2
+                if a > dead and b > dead and g2 > tol * tol * a * b:
+                    d = b - a
+                    h = math.sqrt(d * d + 4 * g2)
+                    u = (2.0 if d >= 0 else -2.0) / (abs(d) + h)
+                    c = 1 / math.sqrt(1 + u * u * g2)
+                    sg = c * u * g
+                    J = np.array([[c, sg], [-np.conj(sg), c]])
+                    W[:, [p, q]] = W[:, [p, q]] @ J
+                    W[[p, q], :] = J.conj().T @ W[[p, q], :]
+                    Q[:, [p, q]] = Q[:, [p, q]] @ J
+                    rot += 1
+        nrot += rot
+        if rot == 0:
+            break
+    return Q, nrot
+
+def block_jacobi(T, b=8, inner=1, tol=None, max_outer=60, sort=False, verbose=False):
+    M, N = T.shape
+    X = T.copy()
+    if sort:
+        X = X[:, np.argsort(-np.linalg.norm(X, axis=0))]
+    tol = tol or math.sqrt(M) * 2.2e-16
+    nb = (N + b - 1) // b
+    nbe = nb + (nb & 1)
+    fro2 = np.linalg.norm(X) ** 2
+    dead = (10 * tol) ** 2 * fro2 / N
+    hist = []
+    for sweep in range(max_outer):
+        dirty = 0
+        for step in range(nbe - 1):
+            for pi in range(nbe // 2):
+                if pi == 0: A_, B_ = nbe - 1, step
+                else: A_, B_ = (step + pi) % (nbe - 1), (step + nbe - 1 - pi) % (nbe - 1)
+                cols = [c for blk in (A_, B_) if blk < nb for c in range(blk * b, min(N, blk * b + b))]
+                if not cols: continue
+                Xs = X[:, cols]
+                W = Xs.conj().T @ Xs
+                d = np.real(np.diag(W))
+                off = np.abs(W) ** 2 > tol * tol * np.outer(d, d)
+                np.fill_diagonal(off, False)
+                off &= np.outer(d > dead, d > dead)
+                if not off.any(): continue
+                dirty += 1
+                Q, _ = jacobi_eig_sweeps(W, tol, inner, dead)
+                X[:, cols] = Xs @ Q
+        hist.append(dirty)
+        if dirty == 0: break
+    s = np.sort(np.linalg.norm(X, axis=0))[::-1]
+    return s, hist
+
+if __name__ == "__main__":
+    chi = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    gauge = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    ths = thetas(chi=chi, gauge=gauge)
+    print("collected", len(ths), "thetas", ths[0].shape)
+    for T in ths[-3:]:
+        sref = np.linalg.svd(T, compute_uv=False)
+        print("cond: s0 %.3e s[chi] %.3e smin %.3e" % (sref[0], sref[chi], sref[-1]))
+        for (b, inner, tol, sort) in [(8, 1, None, False), (8, 1, 1e-13, False), (8, 30, None, False), (8, 30, 1e-13, False), (16, 30, 1e-13, False), (32, 30, 1e-13, False), (8, 30, 1e-13, True)]:
+            s, hist = block_jacobi(T, b=b, inner=inner, tol=tol, sort=sort)
+            print("b=%2d inner=%2d tol=%s sort=%d: outer sweeps %2d  hist %s  relerr %.2e" % (b, inner, tol, sort, len(hist), hist, np.max(np.abs(s - sref) / sref[0])))
+
+def eigh_Q(W):
+    w, Q = np.linalg.eigh(W)
+    # order columns so Q is as close to identity as possible (Jacobi-like, no gratuitous permutation)
+    n = W.shape[0]
+    A = np.abs(Q) ** 2
+    perm = -np.ones(n, dtype=int); used = np.zeros(n, bool)
+    for _ in range(n):
+        i, j = np.unravel_index(np.argmax(np.where(used[None, :] | (perm[:, None] >= 0), -1, A)), A.shape)
+        perm[i] = j; used[j] = True
+    return Q[:, perm]
+
+def block_jacobi_fast(T, b=8, tol=1e-13, max_outer=60, order="rr", qr=False):
+    M, N = T.shape
+    X = T.copy()
+    if qr:
+        # QR preconditioning: T = Q R ; work on L = R^H (lower triangular) columns
+        R = np.linalg.qr(X, mode='r')
+        X = R.conj().T.copy()
+    nb = (N + b - 1) // b
+    nbe = nb + (nb & 1)
+    fro2 = np.linalg.norm(X) ** 2
+    dead = (10 * tol) ** 2 * fro2 / N
+    hist = []
+    for sweep in range(max_outer):
+        dirty = 0
+        for step in range(nbe - 1):
+            for pi in range(nbe // 2):
+                if pi == 0: A_, B_ = nbe - 1, step
+                else: A_, B_ = (step + pi) % (nbe - 1), (step + nbe - 1 - pi) % (nbe - 1)
+                cols = [c for blk in (A_, B_) if blk < nb for c in range(blk * b, min(N, blk * b + b))]
+                if not cols: continue
+                Xs = X[:, cols]
+                W = Xs.conj().T @ Xs
+                d = np.real(np.diag(W))
+                off = np.abs(W) ** 2 > tol * tol * np.outer(d, d)
+                np.fill_diagonal(off, False)
+                off &= np.outer(d > dead, d > dead)
+                if not off.any(): continue
+                dirty += 1
+                X[:, cols] = Xs @ eigh_Q(W)
+        hist.append(dirty)
+        if dirty == 0: break
+    s = np.sort(np.linalg.norm(X, axis=0))[::-1]
+    return s, hist
+
+def study(chi, gauge=0, n=None, depth=None):
+    n = n or (2 * int(math.log2(chi)) + 6)
+    depth = depth or (2 * int(math.log2(chi)) + 8)
+    ths = thetas(n=n, depth=depth, chi=chi, gauge=gauge)
+    print("chi", chi, "collected", len(ths), "thetas", ths[0].shape)
+    for T in ths[-2:]:
+        sref = np.linalg.svd(T, compute_uv=False)
+        print("cond: s0 %.3e s[chi] %.3e smin %.3e" % (sref[0], sref[chi], sref[-1]))
+        for qr in (False, True):
+            for b in (8, 16, 32, 64):
+                if 2 * b > T.shape[1]: continue
+                s, hist = block_jacobi_fast(T, b=b, qr=qr)
+                print("  qr=%d b=%2d nb=%2d: outer sweeps %2d hist %s relerr %.1e" % (qr, b, T.shape[1] // b, len(hist), hist, np.max(np.abs(s - sref)) / sref[0]))

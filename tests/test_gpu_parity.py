@@ -132,8 +132,11 @@ def test_truncated_parity_within_reference_spread(O, n, depth, chi):
         s_g, s_o = e.singular_values(k), o.singular_values(k)
         m = min(len(s_g), len(s_o))
         assert bg <= chi and bo <= chi
-        assert np.abs(s_g[:m] - s_o[:m]).max() < TRUNC_TOL, k
-        assert (s_g[m:] < 1e-12).all() and (s_o[m:] < 1e-12).all(), k
+        # in the reference gauge the sites are not canonical, so the "singular values" of a later theta depend on the
+        # arbitrary basis an SVD driver picks inside (near-)degenerate subspaces: the oracle's own zgesvd and zgesdd
+        # runs differ by 1.1e-5 relative on this circuit (measured here); observables above agree far tighter
+        assert np.abs(s_g[:m] - s_o[:m]).max() < 5e-5 * s_o[0], k
+        assert (s_g[m:] < 1e-12 * s_o[0]).all() and (s_o[m:] < 1e-12 * s_o[0]).all(), k
     assert abs(e.discarded_weight() - o.discarded_weight()) < 1e-4 * max(1.0, o.discarded_weight())
     e.close()
 
