@@ -136,7 +136,11 @@ def test_truncated_parity_within_reference_spread(O, n, depth, chi):
         # arbitrary basis an SVD driver picks inside (near-)degenerate subspaces: the oracle's own zgesvd and zgesdd
         # runs differ by 1.1e-5 relative on this circuit (measured here); observables above agree far tighter
         assert np.abs(s_g[:m] - s_o[:m]).max() < 5e-5 * s_o[0], k
-        assert (s_g[m:] < 1e-12 * s_o[0]).all() and (s_o[m:] < 1e-12 * s_o[0]).all(), k
+        # slices only one side keeps must be weightless.  The bound is sqrt(eps)-level, not eps-level: in the reference gauge
+        # (sqrt(S) into both factors, :1623) a rounding-noise singular value sigma ~ 1e-17..1e-20 leaves sqrt(sigma) ~ 1e-9..1e-10
+        # on each neighbour, which the next SVD on an adjacent bond reports as a "singular value" of that size (observed
+        # 1.3e-10 on the oracle side here); the engine zeroes such numerically-null components instead (null_tol).
+        assert (s_g[m:] < 1e-8 * s_o[0]).all() and (s_o[m:] < 1e-8 * s_o[0]).all(), k
     assert abs(e.discarded_weight() - o.discarded_weight()) < 1e-4 * max(1.0, o.discarded_weight())
     e.close()
 
