@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-peak", action="store_true", help="skip the live cuBLAS DGEMM peak measurement (profiling runs)")
+    ap.add_argument("--no-qr", action="store_true", help="A/B: disable the QR pre-reduction of the SVD")
+    ap.add_argument("--jacobi-tol", type=float, default=0.0, help="A/B: override the Jacobi convergence tolerance")
     ap.add_argument("--prep", default="circuit", choices=["circuit", "random"],
                     help="how the saturated state is made: run the depth-D circuit (default) or load random chi-saturated sites (profiling runs)")
     return ap.parse_args()
@@ -256,6 +258,10 @@ def run_b200(args):
 
     eng = tnqvm_b200.B200MPS(n, max_bond=chi, gauge=args.gauge, device=local)
     stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
+    if args.no_qr:
+        eng.set_option("qr_prereduce", 0)
+    if args.jacobi_tol > 0:
+        eng.set_option("jacobi_tol", args.jacobi_tol)
 
     def timed(fn):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,7 +323,7 @@ def run_b200(args):
     eng.sync()
     pb = eng.stats()
     eng.set_option("profile", 0)
-    ms_theta, ms_svd, ms_wb = (pb[k] - pa[k] for k in ("ms_theta", "ms_svd", "ms_writeback"))
+    ms_theta, ms_svd, ms_wb, ms_qr = (pb[k] - pa[k] for k in ("ms_theta", "ms_svd", "ms_writeback", "ms_qr"))
     jac_launches = None
 
     # ---- e2e: host-resident state, pinned host buffers both ways, observables read back
@@ -399,13 +405,13 @@ def run_b200(args):
             "clocks": clocks,
             "gpu_launches": launches,
             "e2e": e2e,
-            "roofline": {"bound": "tensor", "kernel": "jacobi_step_kernel (SVD phase)", "achieved": svd_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "kernel": "SVD phase: qr_panel/qr_update (pre-reduction) + jacobi_step_kernel", "achieved": svd_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": (svd_tf / fp64_peak) if (svd_tf and fp64_peak) else None, "traffic": traffic,
                          "note": "achieved = LAPACK-equivalent SVD flops (88 M N min(M,N) per gate) / CUDA-event time of the SVD phase; peak = cuBLAS DGEMM 8192^3 measured live in this run (MEASURED_PEAKS.json has no FP64 figure)",
                          "share_of_step": ms_svd / max(1e-9, ms_theta + ms_svd + ms_wb)},
             "roofline_theta": {"bound": "tensor", "kernel": "zgemm_dmma_kernel<theta>", "achieved": th_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                                "frac": (th_tf / fp64_peak) if (th_tf and fp64_peak) else None},
-            "phases_ms_per_step": {"theta": ms_theta / args.steps, "svd": ms_svd / args.steps, "writeback": ms_wb / args.steps,
+            "phases_ms_per_step": {"theta": ms_theta / args.steps, "svd": ms_svd / args.steps, "writeback": ms_wb / args.steps, "qr_prereduce_within_svd": ms_qr / args.steps,
                                    "jacobi_sweeps_per_layer": sweeps_per_layer},
             "circuit": {"name": "brickwork n=%d depth=%d chi<=%d from |0>" % (n, args.depth, chi), "wall_ms": circuit_ms, "gates_1q": n1_0, "gates_2q": n2_0,
                         "gates_2q_per_s": n2_0 / (circuit_ms * 1e-3), "launches": int(st1["launches"] - st0["launches"])},

@@ -80,7 +80,7 @@ struct mps_b200_handle {
   int max_bond = INT_MAX - 1;
   double cutoff = DBL_MIN;
   int gauge = 0, device = 0;
-  int cutoff_on_sqrt = 0, fuse_1q = 1, renorm = 0, profile = 0, layer_batch = 1;
+  int cutoff_on_sqrt = 0, fuse_1q = 1, renorm = 0, profile = 0, layer_batch = 1, use_qr = 1;
   double jacobi_tol = 0.0;   // 0 -> sqrt(M) * eps
   double null_tol = 0.0;     // 0 -> 10 * jacobi tolerance
   int max_sweeps = 40;
@@ -103,7 +103,7 @@ struct mps_b200_handle {
   size_t pin_rb_cap = 0;
   cudaEvent_t ev[6] = {};
   // counters
-  double n2q = 0, n1q = 0, nlayers = 0, nsweeps = 0, nlaunch = 0, ms_theta = 0, ms_svd = 0, ms_wb = 0;
+  double n2q = 0, n1q = 0, nlayers = 0, nsweeps = 0, nlaunch = 0, ms_theta = 0, ms_svd = 0, ms_wb = 0, ms_qr = 0;
 
   // ------------------------------------------------------------------ memory helpers
   void ensure_ws(size_t bytes) {
@@ -290,7 +290,7 @@ struct mps_b200_handle {
     nlayers += 1;
     n2q += B;
 
-    struct Dim { int lo, cl, ch, cr, M, N, tall, Mg, Ng; size_t oT, oG, oSig2, oSigma, oPerm, oSP, oSO, oKeep, oW; };
+    struct Dim { int lo, cl, ch, cr, M, N, tall, Mg, Ng, Mj; size_t oT, oG, oY, oV, oTq, oSig2, oSigma, oPerm, oSP, oSO, oKeep, oW; };
     std::vector<Dim> D(B);
     ws.reset();
     // pass 1: sizes
@@ -303,6 +303,7 @@ struct mps_b200_handle {
       d.tall = d.M >= d.N;
       d.Mg = d.tall ? d.M : d.N;
       d.Ng = d.tall ? d.N : d.M;
+      d.Mj = use_qr ? d.Ng : d.Mg;   // rows of the Jacobi work matrix: R^H is Ng x Ng
     }
     // descriptor block first, then sigma block (contiguous for one read-back), then matrices
     const size_t oGemm = ws.reserve(sizeof(GemmProblem) * B);
@@ -310,6 +311,7 @@ struct mps_b200_handle {
     const size_t oTr = ws.reserve(sizeof(TruncProblem) * B);
     const size_t oGat = ws.reserve(sizeof(GatherProblem) * B);
     const size_t oGemm2 = ws.reserve(sizeof(GemmProblem) * B);
+    const size_t oQr = ws.reserve(sizeof(QrProblem) * B);
     const size_t oFlags = ws.reserve(sizeof(int) * (2 * B + 4) + sizeof(double) * B + 16);   // dirty[B], done[B], remaining, pad, fro2[B]
     const size_t oKeepBlk = ws.reserve((sizeof(int) + 2 * sizeof(double)) * B + 64);
     size_t sig_total = 0;
@@ -332,7 +334,12 @@ struct mps_b200_handle {
       d.oSP = ws.reserve(sizeof(double) * d.Ng);
       d.oSO = ws.reserve(sizeof(double) * d.Ng);
       d.oT = ws.reserve(sizeof(double2) * (size_t)d.Mg * d.Ng);
-      d.oG = ws.reserve(sizeof(double2) * (size_t)d.Mg * d.Ng);
+      d.oG = ws.reserve(sizeof(double2) * (size_t)d.Mj * d.Ng);
+      if (use_qr) {
+        d.oY = ws.reserve(sizeof(double2) * (size_t)d.Mg * d.Ng);
+        d.oV = ws.reserve(sizeof(double2) * (size_t)d.Mg * QR_PB);
+        d.oTq = ws.reserve(sizeof(double2) * QR_PB * QR_PB);
+      }
     }
     const size_t total = ws.off;
     ensure_ws(total);
@@ -345,13 +352,14 @@ struct mps_b200_handle {
     GemmProblem* hG = (GemmProblem*)(st + (oGemm - oGemm));
     JacobiProblem* hJ = (JacobiProblem*)(st + (oJac - oGemm));
     TruncProblem* hT = (TruncProblem*)(st + (oTr - oGemm));
-    int max_tiles = 0, max_pairs = 1, max_steps = 1, maxMg = 1;
+    QrProblem* hQ = (QrProblem*)(st + (oQr - oGemm));
+    int max_tiles = 0, max_pairs = 1, max_steps = 1, maxMg = 1, maxNg = 1;
     for (int b = 0; b < B; ++b) {
       const QGate& g = queue[g2[b]];
       const Dim& d = D[b];
       GemmProblem& p = hG[b];
       p.A = sites[d.lo].d; p.B = sites[d.lo + 1].d;
-      p.C = (double2*)(wb + d.oT); p.C2 = (double2*)(wb + d.oG);
+      p.C = (double2*)(wb + d.oT); p.C2 = (double2*)(wb + (use_qr ? d.oY : d.oG));
       p.M = d.cl; p.N = d.cr; p.K = d.ch;
       p.lda = 2 * d.cl; p.ldb = d.ch; p.ldc = d.Mg;
       p.b_col_stride = 1; p.b_col_off = 0;
@@ -366,14 +374,21 @@ struct mps_b200_handle {
         }
       max_tiles = std::max(max_tiles, gemm_tiles(p.M, p.N, 1));
       JacobiProblem& j = hJ[b];
-      j.G = (double2*)(wb + d.oG); j.M = d.Mg; j.N = d.Ng; j.ldg = d.Mg;
+      j.G = (double2*)(wb + d.oG); j.M = d.Mj; j.N = d.Ng; j.ldg = d.Mj;
+      if (use_qr) {
+        QrProblem& q = hQ[b];
+        q.Y = (double2*)(wb + d.oY); q.V = (double2*)(wb + d.oV); q.T = (double2*)(wb + d.oTq); q.G = j.G;
+        q.M = d.Mg; q.N = d.Ng; q.ldy = d.Mg;
+      }
       j.nb = (d.Ng + 7) / 8;
       j.nbe = (j.nb == 1) ? 1 : ((j.nb + 1) & ~1);
       max_pairs = std::max(max_pairs, j.nb == 1 ? 1 : j.nbe / 2);
       max_steps = std::max(max_steps, j.nb == 1 ? 1 : j.nbe - 1);
       maxMg = std::max(maxMg, d.Mg);
+      maxNg = std::max(maxNg, d.Ng);
       TruncProblem& t = hT[b];
-      t.G = j.G; t.M = d.Mg; t.N = d.Ng; t.ldg = d.Mg; t.tall = d.tall;
+      // with the QR pre-reduction the Jacobi columns carry the singular vectors of the OTHER side (G = R^H)
+      t.G = j.G; t.M = d.Mj; t.N = d.Ng; t.ldg = d.Mj; t.tall = use_qr ? !d.tall : d.tall;
       t.sig2 = (double*)(wb + d.oSig2); t.sigma = (double*)(wb + d.oSigma); t.perm = (int*)(wb + d.oPerm);
       t.scaleP = (double*)(wb + d.oSP); t.scaleO = (double*)(wb + d.oSO);
       t.keep = (int*)(wb + d.oKeep); t.weights = (double*)(wb + d.oW);
@@ -388,6 +403,14 @@ struct mps_b200_handle {
     launch_gemm((const GemmProblem*)(wb + oGemm), B, max_tiles, 0, stream);
     nlaunch += 1;
     if (profile) CK(cudaEventRecord(ev[1], stream));
+
+    // ---- QR pre-reduction: theta_o = Q R, the Jacobi runs on G = R^H
+    if (use_qr) {
+      launch_qr((const QrProblem*)(wb + oQr), B, maxMg, maxNg, stream);
+      nlaunch += qr_launch_count(maxNg);
+      CK(cudaGetLastError());
+    }
+    if (profile) CK(cudaEventRecord(ev[4], stream));
 
     // ---- Jacobi sweeps
     const double eps = 2.220446049250313e-16;
@@ -443,9 +466,24 @@ struct mps_b200_handle {
       GatherProblem& ga = hGa[b];
       GemmProblem& p = hG2[b];
       ga.G = (const double2*)(wb + d.oG); ga.perm = (const int*)(wb + d.oPerm); ga.scale = (const double*)(wb + d.oSP);
-      ga.M = d.Mg; ga.keep = keep; ga.ldg = d.Mg;
+      ga.M = d.Mj; ga.keep = keep; ga.ldg = d.Mj;
       p.alpha = 1.0; p.mode = 0; p.conjT_out = 0; p.b_col_stride = 1; p.b_col_off = 0;
-      if (d.tall) {
+      if (use_qr) {
+        // G = X' = V_o S (Ng x Ng): right singular vectors of theta_o (= T, Mg x Ng) times sigma
+        p.A = (const double2*)(wb + d.oT); p.lda = d.Mg;
+        p.B = (const double2*)(wb + d.oG); p.ldb = d.Mj; p.b_gather = (const int*)(wb + d.oPerm);
+        p.M = d.Mg; p.N = keep; p.K = d.Ng;
+        p.col_scale = (const double*)(wb + d.oSO);
+        if (d.tall) {
+          // theta = T:  hi = f_hi(s)/s * X'[:,perm]^H (keep x N);  lo = T X'[:,perm] diag(f_lo(s)/s^2)  (M x keep)
+          ga.out = sites[d.lo + 1].d; ga.ldo = keep; ga.conjT = 1;
+          p.C = sites[d.lo].d; p.ldc = d.M;
+        } else {
+          // theta^H = T:  lo = X'[:,perm] f_lo(s)/s (M x keep);  hi = (T X'[:,perm] diag(f_hi(s)/s^2))^H  (keep x N)
+          ga.out = sites[d.lo].d; ga.ldo = d.M; ga.conjT = 0;
+          p.C = sites[d.lo + 1].d; p.ldc = keep; p.conjT_out = 1;
+        }
+      } else if (d.tall) {
         // lo = G[:,perm] * sP  (M x keep);  hi = diag(sO) * G[:,perm]^H * theta  (keep x N)
         ga.out = sites[d.lo].d; ga.ldo = d.M; ga.conjT = 0;
         p.A = (const double2*)(wb + d.oG); p.lda = d.Mg; p.a_gather = (const int*)(wb + d.oPerm);
@@ -462,24 +500,25 @@ struct mps_b200_handle {
         p.M = d.M; p.N = keep; p.K = d.Mg;
         p.col_scale = (const double*)(wb + d.oSO);
       }
-      max_rows = std::max(max_rows, d.Mg);
+      max_rows = std::max(max_rows, d.Mj);
       max_keep = std::max(max_keep, keep);
       max_tiles2 = std::max(max_tiles2, gemm_tiles(p.M, p.N, 0));
     }
     CK(cudaMemcpyAsync(wb + oGat, st2, sizeof(GatherProblem) * B, cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(wb + oGemm2, st2 + gaBytes, sizeof(GemmProblem) * B, cudaMemcpyHostToDevice, stream));
     launch_gather((const GatherProblem*)(wb + oGat), B, max_rows, max_keep, stream);
-    launch_gemm((const GemmProblem*)(wb + oGemm2), B, max_tiles2, 1, stream);
+    launch_gemm((const GemmProblem*)(wb + oGemm2), B, max_tiles2, use_qr ? 0 : 1, stream);
     nlaunch += 2;
     CK(cudaGetLastError());
     if (profile) {
       CK(cudaEventRecord(ev[3], stream));
       CK(cudaEventSynchronize(ev[3]));
-      float a = 0, b2 = 0, c = 0;
+      float a = 0, b2 = 0, c = 0, q = 0;
       CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
       CK(cudaEventElapsedTime(&b2, ev[1], ev[2]));
       CK(cudaEventElapsedTime(&c, ev[2], ev[3]));
-      ms_theta += a; ms_svd += b2; ms_wb += c;
+      CK(cudaEventElapsedTime(&q, ev[1], ev[4]));
+      ms_theta += a; ms_svd += b2; ms_wb += c; ms_qr += q;
     }
   }
 
@@ -715,6 +754,9 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     h->has1q.assign(h->ntot, 0);
     h->p1q.resize(h->ntot);
     h->sv.assign(std::max(h->ntot - 1, 1), std::vector<double>{1.0});
+    // developer overrides for A/B runs of the whole test-suite
+    if (const char* e = getenv("MPS_B200_QR")) h->use_qr = atoi(e) != 0;
+    if (const char* e = getenv("MPS_B200_JACOBI_TOL")) h->jacobi_tol = atof(e);
     if (seed) h->rng.seed(seed);
     else { std::random_device rd; h->rng.seed(rd()); }   // RandomEngine.hpp:39-42
     h->reset_state();
@@ -756,6 +798,7 @@ int mps_set_option(mps_handle_t h, const char* key, double value) {
   else if (k == "jacobi_max_sweeps") h->max_sweeps = (int)value;
   else if (k == "profile") h->profile = value != 0;
   else if (k == "layer_batch") { h->flush(); h->layer_batch = value != 0; }
+  else if (k == "qr_prereduce") { h->flush(); h->use_qr = value != 0; }
   else if (k == "max_bond") h->max_bond = value > 0 ? (int)value : INT_MAX - 1;
   else if (k == "svd_cutoff") h->cutoff = value >= 0 ? value : DBL_MIN;
   else if (k == "gauge") h->gauge = (int)value;
@@ -965,8 +1008,8 @@ int mps_resize_site(mps_handle_t h, int k, int dl, int dr, void** dptr) {
 }
 int mps_stats(mps_handle_t h, double* out, int cap) {
   API_BEGIN(h)
-  const double v[8] = {h->n2q, h->n1q, h->nlayers, h->nsweeps, h->nlaunch, h->ms_theta, h->ms_svd, h->ms_wb};
-  for (int i = 0; i < cap && i < 8; ++i) out[i] = v[i];
+  const double v[9] = {h->n2q, h->n1q, h->nlayers, h->nsweeps, h->nlaunch, h->ms_theta, h->ms_svd, h->ms_wb, h->ms_qr};
+  for (int i = 0; i < cap && i < 9; ++i) out[i] = v[i];
   API_END(h)
 }
 

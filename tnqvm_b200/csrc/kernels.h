@@ -35,6 +35,20 @@ void launch_gemm1(const GemmProblem& p, int layout, cudaStream_t s);   // one pr
 int gemm_tiles(int M, int N, int mode);
 
 // ---------------------------------------------------------------------------------------------
+// Batched blocked Householder QR, R factor only (qr_dmma.cu): Y (M x N, M >= N) is overwritten (R in its upper
+// triangle), G (N x N, ld = N) receives R^H.  V (M x QR_PB) and T (QR_PB x QR_PB) are per-matrix scratch.
+constexpr int QR_PB = 16;
+struct QrProblem {
+  double2* Y;
+  double2* V;
+  double2* T;
+  double2* G;
+  int M, N, ldy;
+};
+void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaStream_t s);
+int qr_launch_count(int max_n);
+
+// ---------------------------------------------------------------------------------------------
 // Batched one-sided Jacobi SVD (block Hestenes): G (M x N, M >= N) -> G V with orthogonal columns.
 struct JacobiProblem {
   double2* G;

@@ -1,0 +1,319 @@
+// Batched blocked Householder QR (R factor only), complex128, sm_100a: the tensor-core pre-reduction of the
+// two-qubit-gate SVD (the reference calls LAPACK zgesvd/zgesdd through exatn::decomposeTensorSVDLRSync,
+// ExaTnMpsVisitor.cpp:1619-1627).
+//
+// theta_o (M x N, M >= N) = Q R.  Only R is kept: the one-sided Jacobi then runs on G = R^H (N x N), which
+//   (a) shrinks the Jacobi rows from M to N when theta is rectangular, and
+//   (b) preconditions it: (R^H)^H (R^H) = R R^H is one LR-Cholesky step closer to diagonal than theta^H theta, so
+//       the number of Jacobi sweeps drops ~3x on the graded spectra of truncated MPS bonds.
+// Q is never formed or applied: the singular vectors come back from theta itself (engine.cu write-back).
+//
+// Per panel of PB = 16 columns, two launches over the whole batch:
+//   qr_panel_kernel   one CTA per matrix; the panel lives in shared memory, warp c owns column c; per column one
+//                     reflector (zlarfg convention, H = I - tau v v^H) and its application to the later panel columns
+//                     with warp-shuffle reductions; then the compact-WY factor T (zlarft, forward/columnwise).
+//   qr_update_kernel  one CTA per 32 trailing columns: C <- (I - V T V^H)^H C = C - V (T^H (V^H C)), both products
+//                     on the FP64 tensor cores (DMMA m8n8k4), complex arithmetic as 4 real MMAs.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace mpsb200 {
+namespace {
+
+constexpr int PB = QR_PB;            // panel width
+constexpr int PT = 32 * PB;          // panel-kernel threads: one warp per panel column
+constexpr int PANEL_SMEM_CAP = 208 * 1024;
+constexpr int SLAB = 32;             // trailing columns per update CTA
+constexpr int UT = 128;              // update-kernel threads
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {   // conj(a) * b
+  return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(PT, 1) qr_panel_kernel(const QrProblem* __restrict__ probs, int k) {
+  const QrProblem P = probs[blockIdx.x];
+  const int c0 = k * PB;
+  if (c0 >= P.N) return;
+  const int pw = min(PB, P.N - c0);
+  const int r0 = c0, mk = P.M - r0;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* sp = reinterpret_cast<double2*>(smem_raw);
+  __shared__ double2 s_tau[PB];
+  __shared__ double2 sS[PB][PB + 1];
+  __shared__ double2 sT[PB][PB + 1];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double2* gp = P.Y + r0 + (size_t)P.ldy * c0;   // panel in global memory
+  const bool in_smem = (size_t)mk * pw * sizeof(double2) <= (size_t)PANEL_SMEM_CAP;
+  double2* Pn;
+  int ld;
+  if (in_smem) {
+    Pn = sp; ld = mk;
+    for (int c = warp; c < pw; c += PB)
+      for (int i = lane; i < mk; i += 32) sp[i + (size_t)mk * c] = gp[i + (size_t)P.ldy * c];
+  } else {
+    Pn = gp; ld = P.ldy;
+  }
+  __syncthreads();
+
+  for (int j = 0; j < pw; ++j) {
+    if (warp == j) {
+      double2* x = Pn + (size_t)ld * j;
+      double s = 0.0;
+      for (int i = j + 1 + lane; i < mk; i += 32) { const double2 v = x[i]; s += v.x * v.x + v.y * v.y; }
+      s = warp_sum(s);
+      const double2 alpha = x[j];
+      double2 tau = make_double2(0.0, 0.0);
+      if (s > 0.0) {
+        // zlarfg: beta = -sign(re alpha) * ||(alpha, x)||, tau = (beta - alpha)/beta, v = x / (alpha - beta)
+        const double an = sqrt(alpha.x * alpha.x + alpha.y * alpha.y + s);
+        const double beta = alpha.x >= 0.0 ? -an : an;
+        tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
+        const double dx = alpha.x - beta, dy = alpha.y;
+        const double dn = 1.0 / (dx * dx + dy * dy);
+        const double2 inv = make_double2(dx * dn, -dy * dn);
+        for (int i = j + 1 + lane; i < mk; i += 32) x[i] = cmul(x[i], inv);
+        if (lane == 0) x[j] = make_double2(beta, 0.0);
+      }
+      if (lane == 0) s_tau[j] = tau;
+    }
+    __syncthreads();
+    if (warp > j && warp < pw) {
+      const double2 tau = s_tau[j];
+      if (tau.x != 0.0 || tau.y != 0.0) {
+        const double2* v = Pn + (size_t)ld * j;
+        double2* a = Pn + (size_t)ld * warp;
+        double wr = 0.0, wi = 0.0;
+        for (int i = j + 1 + lane; i < mk; i += 32) { const double2 t = cmulc(v[i], a[i]); wr += t.x; wi += t.y; }
+        wr = warp_sum(wr); wi = warp_sum(wi);
+        const double2 aj = a[j];
+        const double2 w = make_double2(wr + aj.x, wi + aj.y);           // v^H a, v(j) = 1
+        const double2 f = cmul(make_double2(tau.x, -tau.y), w);         // conj(tau) * w :  H^H a = a - conj(tau) v (v^H a)
+        for (int i = j + 1 + lane; i < mk; i += 32) { const double2 t = cmul(f, v[i]); a[i].x -= t.x; a[i].y -= t.y; }
+        if (lane == 0) a[j] = make_double2(aj.x - f.x, aj.y - f.y);
+      }
+    }
+    __syncthreads();
+  }
+
+  // S = V^H V (strict upper part), V unit lower trapezoidal
+  for (int pr = warp; pr < PB * PB; pr += PB) {
+    const int a = pr / PB, b = pr % PB;
+    if (a < b && b < pw) {
+      const double2* va = Pn + (size_t)ld * a;
+      const double2* vb = Pn + (size_t)ld * b;
+      double sr = 0.0, si = 0.0;
+      for (int i = b + 1 + lane; i < mk; i += 32) { const double2 t = cmulc(va[i], vb[i]); sr += t.x; si += t.y; }
+      sr = warp_sum(sr); si = warp_sum(si);
+      if (lane == 0) { const double2 h = va[b]; sS[a][b] = make_double2(sr + h.x, si - h.y); }   // + conj(V[b][a]) * 1
+    }
+  }
+  for (int i = tid; i < PB * PB; i += PT) sT[i / PB][i % PB] = make_double2(0.0, 0.0);
+  __syncthreads();
+  // zlarft (forward, columnwise): T(j,j) = tau_j ; T(0:j, j) = -tau_j * T(0:j,0:j) * S(0:j, j)
+  if (warp == 0) {
+    for (int j = 0; j < pw; ++j) {
+      const double2 tau = s_tau[j];
+      if (lane < j) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int l = lane; l < j; ++l) { const double2 t = cmul(sT[lane][l], sS[l][j]); acc.x += t.x; acc.y += t.y; }
+        const double2 t = cmul(tau, acc);
+        sT[lane][j] = make_double2(-t.x, -t.y);
+      }
+      if (lane == j) sT[j][j] = tau;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < PB * PB; i += PT) P.T[i] = sT[i % PB][i / PB];   // column-major PB x PB
+  // clean reflector block for the update kernel: V (mk x PB, ld = P.M), unit diagonal, zeros above and beyond pw
+  for (int c = warp; c < PB; c += PB) {
+    double2* vout = P.V + (size_t)P.M * c;
+    for (int i = lane; i < mk; i += 32) {
+      double2 v = make_double2(0.0, 0.0);
+      if (c < pw) {
+        if (i == c) v = make_double2(1.0, 0.0);
+        else if (i > c) v = Pn[i + (size_t)ld * c];
+      }
+      vout[i] = v;
+    }
+  }
+  if (in_smem) {
+    for (int c = warp; c < pw; c += PB)
+      for (int i = lane; i < mk; i += 32) gp[i + (size_t)P.ldy * c] = sp[i + (size_t)mk * c];
+  }
+}
+
+// C <- C - V * (T^H * (V^H C)) on a slab of SLAB trailing columns
+__global__ void __launch_bounds__(UT, 4) qr_update_kernel(const QrProblem* __restrict__ probs, int k) {
+  const QrProblem P = probs[blockIdx.y];
+  const int c0 = k * PB;
+  if (c0 >= P.N) return;
+  const int pw = min(PB, P.N - c0);
+  const int t0 = c0 + pw;
+  const int col0 = t0 + blockIdx.x * SLAB;
+  if (col0 >= P.N) return;
+  const int ncol = min(SLAB, P.N - col0);
+  const int r0 = c0, mk = P.M - r0;
+  const double2* __restrict__ V = P.V;
+  const int ldv = P.M, ldy = P.ldy;
+  double2* C = P.Y + r0 + (size_t)ldy * col0;
+
+  __shared__ double2 sW[4][PB][SLAB + 1];
+  __shared__ double2 sW2[PB][SLAB + 1];
+  __shared__ double2 sTm[PB][PB + 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lk = lane & 3;
+  for (int i = tid; i < PB * PB; i += UT) sTm[i % PB][i / PB] = P.T[i];
+
+  // ---------------- phase 1: W = V^H C  (PB x SLAB), K = mk rows split over the warps
+  {
+    double wre[2][4][2], wim[2][4][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) { wre[m][n][0] = wre[m][n][1] = wim[m][n][0] = wim[m][n][1] = 0.0; }
+    const int nch = (mk + 3) >> 2;
+    for (int ch = warp; ch < nch; ch += 4) {
+      const int row = 4 * ch + lk;
+      const bool rok = row < mk;
+      double2 a[2], b[4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) a[m] = rok ? V[row + (size_t)ldv * (8 * m + lr)] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) b[n] = (rok && 8 * n + lr < ncol) ? C[row + (size_t)ldy * (8 * n + lr)] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const double ar = a[m].x, ai = a[m].y, nai = -a[m].y;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          dmma884(wre[m][n][0], wre[m][n][1], ar, b[n].x);
+          dmma884(wre[m][n][0], wre[m][n][1], ai, b[n].y);
+          dmma884(wim[m][n][0], wim[m][n][1], ar, b[n].y);
+          dmma884(wim[m][n][0], wim[m][n][1], nai, b[n].x);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) sW[warp][8 * m + lr][8 * n + 2 * lk + e] = make_double2(wre[m][n][e], wim[m][n][e]);
+  }
+  __syncthreads();
+  // ---------------- phase 2: W2 = T^H (sum of the four partial W)
+  for (int i = tid; i < PB * SLAB; i += UT) {
+    const int r = i / SLAB, c = i % SLAB;
+    const double2 a = sW[0][r][c], b = sW[1][r][c], cc = sW[2][r][c], d = sW[3][r][c];
+    sW[0][r][c] = make_double2(a.x + b.x + cc.x + d.x, a.y + b.y + cc.y + d.y);
+  }
+  __syncthreads();
+  for (int i = tid; i < PB * SLAB; i += UT) {
+    const int r = i / SLAB, c = i % SLAB;
+    double2 acc = make_double2(0.0, 0.0);
+    for (int l = 0; l <= r; ++l) { const double2 t = cmulc(sTm[l][r], sW[0][l][c]); acc.x += t.x; acc.y += t.y; }
+    sW2[r][c] = acc;
+  }
+  __syncthreads();
+  // ---------------- phase 3: C -= V W2
+  {
+    const int nch = (mk + 7) >> 3;
+    for (int ch = warp; ch < nch; ch += 4) {
+      const int row = 8 * ch + lr;
+      const bool rok = row < mk;
+      double2 a[4];
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) a[kc] = rok ? V[row + (size_t)ldv * (4 * kc + lk)] : make_double2(0.0, 0.0);
+      double cre[4][2], cim[4][2];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * n + 2 * lk + e;
+          const double2 v = (rok && col < ncol) ? C[row + (size_t)ldy * col] : make_double2(0.0, 0.0);
+          cre[n][e] = v.x; cim[n][e] = v.y;
+        }
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        const double nar = -a[kc].x, ai = a[kc].y, nai = -a[kc].y;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const double2 b = sW2[4 * kc + lk][8 * n + lr];
+          dmma884(cre[n][0], cre[n][1], nar, b.x);
+          dmma884(cre[n][0], cre[n][1], ai, b.y);
+          dmma884(cim[n][0], cim[n][1], nar, b.y);
+          dmma884(cim[n][0], cim[n][1], nai, b.x);
+        }
+      }
+      if (rok) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = 8 * n + 2 * lk + e;
+            if (col < ncol) C[row + (size_t)ldy * col] = make_double2(cre[n][e], cim[n][e]);
+          }
+      }
+    }
+  }
+}
+
+// G = R^H : G[i + N j] = conj(Y[j + ldy i]) for j <= i, else 0
+__global__ void __launch_bounds__(256) qr_rh_kernel(const QrProblem* __restrict__ probs) {
+  const QrProblem P = probs[blockIdx.z];
+  const int N = P.N;
+  const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  if (i0 >= N || j0 >= N) return;
+  __shared__ double2 tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  // read Y[j0 + tx][i0 + r]  (rows j contiguous)
+  for (int r = ty; r < 32; r += 8) {
+    const int j = j0 + tx, i = i0 + r;
+    double2 v = make_double2(0.0, 0.0);
+    if (i < N && j < N && j <= i) { v = P.Y[j + (size_t)P.ldy * i]; v.y = -v.y; }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + tx, j = j0 + r;
+    if (i < N && j < N) P.G[i + (size_t)N * j] = tile[tx][r];
+  }
+}
+
+}  // namespace
+
+void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaStream_t s) {
+  if (batch <= 0 || max_n <= 0) return;
+  // the panel is staged in shared memory whenever it fits (the kernel applies the same test per matrix)
+  const size_t want = (size_t)max_m * PB * sizeof(double2);
+  const int smem = (int)(want < (size_t)PANEL_SMEM_CAP ? want : (size_t)PANEL_SMEM_CAP);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_CAP);
+    attr_set = true;
+  }
+  const int npanels = (max_n + PB - 1) / PB;
+  for (int k = 0; k < npanels; ++k) {
+    qr_panel_kernel<<<batch, PT, smem, s>>>(d_probs, k);
+    const int ntr = max_n - (k + 1) * PB;
+    if (ntr > 0) {
+      dim3 grid((ntr + SLAB - 1) / SLAB, batch);
+      qr_update_kernel<<<grid, UT, 0, s>>>(d_probs, k);
+    }
+  }
+  dim3 g2((max_n + 31) / 32, (max_n + 31) / 32, batch);
+  qr_rh_kernel<<<g2, 256, 0, s>>>(d_probs);
+}
+int qr_launch_count(int max_n) {
+  const int npanels = (max_n + PB - 1) / PB;
+  return 2 * npanels;   // panels + updates (the last panel has no update) + the R^H transpose
+}
+
+}  // namespace mpsb200
