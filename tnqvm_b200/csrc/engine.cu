@@ -102,6 +102,17 @@ struct mps_b200_handle {
   char* pin_rb = nullptr;
   size_t pin_rb_cap = 0;
   cudaEvent_t ev[6] = {};
+  // Jacobi groups: the matrices of a layer are split over NGROUP streams so that the Gram / rotate / apply phases of
+  // different groups overlap on the SMs (one stream alone leaves the DMMA pipe idle during the serial rotation phase)
+  static constexpr int NGROUP = 4, GDEPTH = 2;
+  int jacobi_groups = 1;
+  int jacobi_persistent = 1;   // one persistent dataflow launch per sweep (jacobi_sweep_kernel) instead of one launch per step
+  int sm_count = 148;
+  int stagger_ns = 0;
+  cudaStream_t gstream[NGROUP] = {};
+  cudaEvent_t gev[NGROUP][GDEPTH] = {};
+  cudaEvent_t gend[NGROUP] = {}, gstart = nullptr;
+  int* pin_rem = nullptr;   // [NGROUP][GDEPTH] pinned
   // counters
   double n2q = 0, n1q = 0, nlayers = 0, nsweeps = 0, nlaunch = 0, ms_theta = 0, ms_svd = 0, ms_wb = 0, ms_qr = 0;
 
@@ -287,6 +298,14 @@ struct mps_b200_handle {
     run_1q(p1);
     if (g2.empty()) return;
     const int B = (int)g2.size();
+    const int NG = std::max(1, std::min({jacobi_groups, (int)NGROUP, B}));
+    if (NG > 1) {   // interleave the gates over the groups (chain ends are small, the middle is large): group g = b % NG
+      std::vector<int> r;
+      r.reserve(B);
+      for (int g = 0; g < NG; ++g)
+        for (int b = g; b < B; b += NG) r.push_back(g2[b]);
+      g2.swap(r);
+    }
     nlayers += 1;
     n2q += B;
 
@@ -312,6 +331,9 @@ struct mps_b200_handle {
     const size_t oGat = ws.reserve(sizeof(GatherProblem) * B);
     const size_t oGemm2 = ws.reserve(sizeof(GemmProblem) * B);
     const size_t oQr = ws.reserve(sizeof(QrProblem) * B);
+    int pstride = 2;   // progress flags per matrix of the persistent sweep kernel: one per 8-column block
+    for (int b = 0; b < B; ++b) pstride = std::max(pstride, ((D[b].Ng + 7) / 8 + 1) & ~1);
+    const size_t oProg = ws.reserve(sizeof(int) * ((size_t)B * pstride + max_sweeps + 4));
     const size_t oFlags = ws.reserve(sizeof(int) * (2 * B + 4) + sizeof(double) * B + 16);   // dirty[B], done[B], remaining, pad, fro2[B]
     const size_t oKeepBlk = ws.reserve((sizeof(int) + 2 * sizeof(double)) * B + 64);
     size_t sig_total = 0;
@@ -422,13 +444,80 @@ struct mps_b200_handle {
     launch_fro2((const JacobiProblem*)(wb + oJac), B, d_fro2, stream);
     nlaunch += 1;
     int sweep = 0;
-    for (; sweep < max_sweeps; ++sweep) {
-      for (int s = 0; s < max_steps; ++s) launch_jacobi_step((const JacobiProblem*)(wb + oJac), B, max_pairs, s, tol2, dead2, d_fro2, d_dirty, d_done, stream);
-      launch_jacobi_check(B, d_dirty, d_done, d_rem, stream);
-      nlaunch += max_steps + 1;
-      CK(cudaMemcpyAsync(h_rem, d_rem, sizeof(int), cudaMemcpyDeviceToHost, stream));
-      CK(cudaStreamSynchronize(stream));
-      if (*h_rem == 0) { ++sweep; break; }
+    static const bool trace = getenv("MPS_B200_TRACE") != nullptr;   // developer aid: per-sweep progress on stderr
+    if (jacobi_persistent && NG == 1) {
+      int* d_prog = (int*)(wb + oProg);
+      int* d_cnt = d_prog + (size_t)B * pstride;
+      if (trace) CK(cudaEventRecord(ev[5], stream));
+      for (; sweep < max_sweeps; ++sweep) {
+        launch_jacobi_sweep((const JacobiProblem*)(wb + oJac), B, max_pairs, max_steps, sweep * max_steps, tol2, dead2, d_fro2, d_dirty,
+                            d_done, d_prog, pstride, d_cnt + sweep, d_rem + 1, sm_count * 4, stagger_ns, stream);
+        launch_jacobi_check(B, d_dirty, d_done, d_rem, stream);
+        nlaunch += 2;
+        CK(cudaMemcpyAsync(h_rem, d_rem, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (trace) CK(cudaEventRecord(ev[3], stream));
+        CK(cudaStreamSynchronize(stream));
+        if (h_rem[1] != 0) throw std::runtime_error("internal: Jacobi dataflow wait timed out");
+        if (trace) {
+          float ms = 0;
+          CK(cudaEventElapsedTime(&ms, ev[5], ev[3]));
+          fprintf(stderr, "[mps_b200 trace] layer %d B=%d sweep %d: %.3f ms, %d matrices still rotating\n", (int)nlayers, B, sweep, ms, *h_rem);
+          CK(cudaEventRecord(ev[5], stream));
+        }
+        if (*h_rem == 0) { ++sweep; break; }
+      }
+    } else
+    {
+      // contiguous slices of the (interleaved) batch per group
+      int goff[NGROUP + 1], gpairs[NGROUP], gsteps[NGROUP];
+      goff[0] = 0;
+      for (int g = 0; g < NG; ++g) {
+        const int cnt = (B - g + NG - 1) / NG;
+        goff[g + 1] = goff[g] + cnt;
+        gpairs[g] = 1; gsteps[g] = 1;
+        for (int b = goff[g]; b < goff[g + 1]; ++b) {
+          gpairs[g] = std::max(gpairs[g], hJ[b].nb == 1 ? 1 : hJ[b].nbe / 2);
+          gsteps[g] = std::max(gsteps[g], hJ[b].nb == 1 ? 1 : hJ[b].nbe - 1);
+        }
+      }
+      CK(cudaEventRecord(gstart, stream));
+      const JacobiProblem* dJ = (const JacobiProblem*)(wb + oJac);
+      int enq[NGROUP] = {}, seen[NGROUP] = {};
+      bool fin[NGROUP] = {};
+      auto enqueue = [&](int g) {
+        cudaStream_t gs = gstream[g];
+        const int o = goff[g], nb = goff[g + 1] - goff[g];
+        for (int st_ = 0; st_ < gsteps[g]; ++st_)
+          launch_jacobi_step(dJ + o, nb, gpairs[g], st_, tol2, dead2, d_fro2 + o, d_dirty + o, d_done + o, gs);
+        launch_jacobi_check(nb, d_dirty + o, d_done + o, d_rem + g, gs);
+        nlaunch += gsteps[g] + 1;
+        const int slot = enq[g] % GDEPTH;
+        CK(cudaMemcpyAsync(pin_rem + g * GDEPTH + slot, d_rem + g, sizeof(int), cudaMemcpyDeviceToHost, gs));
+        CK(cudaEventRecord(gev[g][slot], gs));
+        ++enq[g];
+      };
+      for (int g = 0; g < NG; ++g) {
+        CK(cudaStreamWaitEvent(gstream[g], gstart, 0));
+        for (int d = 0; d < GDEPTH && d < max_sweeps; ++d) enqueue(g);
+      }
+      int active = NG;
+      while (active > 0) {
+        for (int g = 0; g < NG; ++g) {
+          if (fin[g]) continue;
+          const int slot = seen[g] % GDEPTH;
+          CK(cudaEventSynchronize(gev[g][slot]));
+          const int rem = pin_rem[g * GDEPTH + slot];
+          ++seen[g];
+          if (trace) fprintf(stderr, "[mps_b200 trace] layer %d B=%d group %d sweep %d: %d matrices still rotating\n", (int)nlayers, B, g, seen[g] - 1, rem);
+          if (rem == 0 || seen[g] >= max_sweeps) { fin[g] = true; --active; }
+          else if (enq[g] < max_sweeps) enqueue(g);
+        }
+      }
+      for (int g = 0; g < NG; ++g) {
+        sweep = std::max(sweep, seen[g]);
+        CK(cudaEventRecord(gend[g], gstream[g]));   // behind any speculative (no-op) sweep still queued
+        CK(cudaStreamWaitEvent(stream, gend[g], 0));
+      }
     }
     nsweeps += sweep;
     if (profile) CK(cudaEventRecord(ev[2], stream));
@@ -750,12 +839,25 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     h->gauge = gauge; h->device = device;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+    for (int g = 0; g < mps_b200_handle::NGROUP; ++g) {
+      CK(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+      for (auto& ev : h->gev[g]) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->gend[g], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&h->gstart, cudaEventDisableTiming));
+    CK(cudaMallocHost(&h->pin_rem, sizeof(int) * mps_b200_handle::NGROUP * mps_b200_handle::GDEPTH));
     h->sites.resize(h->ntot);
     h->has1q.assign(h->ntot, 0);
     h->p1q.resize(h->ntot);
     h->sv.assign(std::max(h->ntot - 1, 1), std::vector<double>{1.0});
     // developer overrides for A/B runs of the whole test-suite
     if (const char* e = getenv("MPS_B200_QR")) h->use_qr = atoi(e) != 0;
+    if (const char* e = getenv("MPS_B200_GROUPS")) h->jacobi_groups = std::max(1, atoi(e));
+    if (const char* e = getenv("MPS_B200_PERSISTENT")) h->jacobi_persistent = atoi(e) != 0;
+    if (const char* e = getenv("MPS_B200_MAX_SWEEPS")) h->max_sweeps = std::max(1, atoi(e));
+    if (const char* e = getenv("MPS_B200_STAGGER_NS")) h->stagger_ns = atoi(e);
+    if (const char* e = getenv("MPS_B200_DBG_MODE")) jacobi_set_debug_mode(atoi(e));
+    h->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("MPS_B200_JACOBI_TOL")) h->jacobi_tol = atof(e);
     if (seed) h->rng.seed(seed);
     else { std::random_device rd; h->rng.seed(rd()); }   // RandomEngine.hpp:39-42
@@ -773,11 +875,19 @@ int mps_destroy(mps_handle_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (getenv("MPS_B200_DBG_MODE")) jacobi_print_phase_timing();
   for (auto& s : h->sites) if (s.d) cudaFree(s.d);
   if (h->ws.base) cudaFree(h->ws.base);
   for (int i = 0; i < 2; ++i) if (h->pin[i]) cudaFreeHost(h->pin[i]);
   if (h->pin_rb) cudaFreeHost(h->pin_rb);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  for (int g = 0; g < mps_b200_handle::NGROUP; ++g) {
+    if (h->gstream[g]) { cudaStreamSynchronize(h->gstream[g]); cudaStreamDestroy(h->gstream[g]); }
+    for (auto& ev : h->gev[g]) if (ev) cudaEventDestroy(ev);
+    if (h->gend[g]) cudaEventDestroy(h->gend[g]);
+  }
+  if (h->gstart) cudaEventDestroy(h->gstart);
+  if (h->pin_rem) cudaFreeHost(h->pin_rem);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -799,6 +909,8 @@ int mps_set_option(mps_handle_t h, const char* key, double value) {
   else if (k == "profile") h->profile = value != 0;
   else if (k == "layer_batch") { h->flush(); h->layer_batch = value != 0; }
   else if (k == "qr_prereduce") { h->flush(); h->use_qr = value != 0; }
+  else if (k == "jacobi_groups") { h->flush(); h->jacobi_groups = std::max(1, (int)value); }
+  else if (k == "jacobi_persistent") { h->flush(); h->jacobi_persistent = value != 0; }
   else if (k == "max_bond") h->max_bond = value > 0 ? (int)value : INT_MAX - 1;
   else if (k == "svd_cutoff") h->cutoff = value >= 0 ? value : DBL_MIN;
   else if (k == "gauge") h->gauge = (int)value;

@@ -15,12 +15,16 @@
 // one GEMM against the saved theta (see engine.cu), which is what keeps the kernel at 16 columns/CTA.
 #include "kernels.h"
 #include "ptx.cuh"
+#include <algorithm>
+#include <cstdio>
 
 namespace mpsb200 {
 namespace {
 
 constexpr int JT = 128;     // threads per CTA (4 warps)
 constexpr int WLD = 17;     // padded leading dimension of the 16x16 shared matrices
+__device__ unsigned long long g_phase_cycles[8];   // developer timing (g_dbg_mode == 10): A, reduce+test, B, C, wait, tasks
+__device__ int g_dbg_mode = 0;   // developer switches: 4 = rotate the pairs inside a block at every step (A/B run); 10 = per-phase clock64 timing
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {   // conj(a) * b
@@ -30,28 +34,30 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 rmul(double r, double2 a) { return make_double2(r * a.x, r * a.y); }
 
-__global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem* __restrict__ probs, int step, double tol2, double dead2,
-                                                            const double* __restrict__ fro2, int* __restrict__ dirty,
-                                                            const int* __restrict__ done) {
-  const int mat = blockIdx.y;
-  if (done[mat]) return;
-  const JacobiProblem P = probs[mat];
-  const int npairs = (P.nb == 1) ? 1 : P.nbe / 2;
-  const int pi = blockIdx.x;
-  if (pi >= npairs) return;
-  int blkA = 0, blkB = -1;
+// round-robin tournament: the pair of 8-column blocks that task `pi` of step `step` owns (-1 = phantom block)
+__device__ __forceinline__ bool pair_blocks(const JacobiProblem& P, int step, int pi, int& blkA, int& blkB, bool& within) {
+  blkA = 0; blkB = -1; within = true;
   if (P.nb > 1) {
     const int nm1 = P.nbe - 1;
     const int s = step % nm1;
+    within = (s == 0);
     if (pi == 0) { blkA = nm1; blkB = s; }
     else { blkA = (s + pi) % nm1; blkB = (s + nm1 - pi) % nm1; }
     if (blkA >= P.nb) blkA = -1;
     if (blkB >= P.nb) blkB = -1;
     if (blkA < 0) { blkA = blkB; blkB = -1; }
-    if (blkA < 0) return;
+    if (blkA < 0) return false;
   }
+  return true;
+}
+
+// one pair task: Gram (phase A), rotations (phase B), apply (phase C) on the 16 columns of blocks (blkA, blkB).
+// All exits are uniform over the CTA.  Loads of G bypass L1 (ld.global.cg): inside the persistent sweep kernel the
+// columns were last written by a CTA on another SM.
+__device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int blkA, int blkB, bool within, double tol2, double dead2,
+                                          const double* __restrict__ fro2, int* __restrict__ dirty) {
   const int M = P.M, N = P.N, ldg = P.ldg;
-  double2* __restrict__ G = P.G;
+  double2* G = P.G;
   // columns whose squared norm is below dead_abs (<= (null_tol * sigma_max)^2) are numerically null: they are zeroed at
   // write-back and never rotated, so rank-deficient thetas do not spend sweeps orthogonalising rounding noise
   const double dead_abs = dead2 * fro2[mat] / (double)N;
@@ -74,6 +80,9 @@ __global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem*
   }
   if (tid == 0) s_need = 0;
   __syncthreads();
+  const bool timing = (g_dbg_mode == 10) && tid == 0;
+  long long tA = 0, tB = 0, tC = 0, tD = 0;
+  if (timing) tA = clock64();
 
   // ------------------------------------------------------------------ phase A: Gram matrix on DMMA
   {
@@ -90,8 +99,8 @@ __global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem*
       for (int u = 0; u < UN; ++u) {
         const int row = 4 * (base + u) + rsub;
         const bool ok = row < M;
-        x0[u] = (ok && p0) ? p0[row] : make_double2(0.0, 0.0);
-        x1[u] = (ok && p1) ? p1[row] : make_double2(0.0, 0.0);
+        x0[u] = (ok && p0) ? __ldcg(p0 + row) : make_double2(0.0, 0.0);
+        x1[u] = (ok && p1) ? __ldcg(p1 + row) : make_double2(0.0, 0.0);
       }
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
@@ -118,6 +127,7 @@ __global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem*
     s_red[warp][6][e0] = q01[0]; s_red[warp][6][e0 + 1] = q01[1];
   }
   __syncthreads();
+  if (timing) tB = clock64();
   for (int i = tid; i < 7 * 64; i += JT) {
     const int t = i >> 6, e = i & 63;
     s_red[0][t][e] = s_red[0][t][e] + s_red[1][t][e] + s_red[2][t][e] + s_red[3][t][e];
@@ -135,12 +145,12 @@ __global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem*
     sQ[p * WLD + q] = make_double2(p == q ? 1.0 : 0.0, 0.0);
   }
   __syncthreads();
-  // fresh-Gram convergence test over all pairs of the 16 columns
+  // fresh-Gram convergence test over the pairs this task is responsible for
   {
     int need = 0;
     for (int i = tid; i < 256; i += JT) {
       const int p = i >> 4, q = i & 15;
-      if (p < q) {
+      if (p < q && (within || (p < 8 && q >= 8))) {   // pairs inside a block belong to the first step of the tournament
         const double a = sW[p * WLD + p].x, b = sW[q * WLD + q].x;
         const double2 g = sW[p * WLD + q];
         if (a > dead_abs && b > dead_abs && (g.x * g.x + g.y * g.y) > tol2 * a * b) need = 1;
@@ -149,40 +159,50 @@ __global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem*
     if (need) s_need = 1;   // benign race: all writers store 1
   }
   __syncthreads();
+  if (timing) { tC = clock64(); atomicAdd(&g_phase_cycles[0], (unsigned long long)(tB - tA)); atomicAdd(&g_phase_cycles[1], (unsigned long long)(tC - tB)); atomicAdd(&g_phase_cycles[5], 1ull); }
   if (!s_need) return;
   if (tid == 0) dirty[mat] = 1;
 
-  // ------------------------------------------------------------------ phase B: Jacobi sweep on W (warp 0)
-  if (warp == 0) {
-    for (int r = 0; r < 15; ++r) {
-      bool rot = false;
-      if (lane < 8) {
-        int p = (lane == 0) ? 15 : (r + lane) % 15;
-        int q = (r + 15 - lane) % 15;
-        if (p > q) { const int t = p; p = q; q = t; }
+  // ------------------------------------------------------------------ phase B: Jacobi rotations on W (all four warps)
+  // Round r rotates 8 disjoint column pairs.  Rounds 0-7 are the bipartite schedule over the cross pairs (i, 8 + (i+r)%8);
+  // rounds 8-14 (only when `within`: the first step of a tournament) are the two 8-column round-robins of the pairs
+  // inside each block, which every later step of the sweep leaves alone.  Lanes 0-7 of warp 0 compute the rotations
+  // (two rsqrt, no division or sqrt), warps 0-1 apply them to W two-sidedly, warps 2-3 accumulate Q.
+  {
+    const int nrounds = within ? 15 : 8;
+    for (int r = 0; r < nrounds; ++r) {
+      int rot = 0;
+      if (tid < 8) {
+        int p, q;
+        if (r < 8) { p = tid; q = 8 + ((tid + r) & 7); }
+        else {
+          const int w = r - 8, l = tid & 3, off = (tid >> 2) * 8;
+          p = (l == 0) ? 7 : (w + l) % 7;
+          q = (w + 7 - l) % 7;
+          if (p > q) { const int t = p; p = q; q = t; }
+          p += off; q += off;
+        }
         const double a = sW[p * WLD + p].x, b = sW[q * WLD + q].x;
         const double2 g = sW[p * WLD + q];
         const double g2 = g.x * g.x + g.y * g.y;
         double c = 1.0;
         double2 sg = make_double2(0.0, 0.0);
         if (a > dead_abs && b > dead_abs && g2 > tol2 * a * b) {
-          rot = true;
+          rot = 1;
+          // cos 2t = |d|/h, sin 2t = 2|g|/h  (|t| <= pi/4):  c = sqrt((1 + |d|/h)/2),  s = sign(d) g / (h c)
           const double d = b - a;
-          const double h = sqrt(d * d + 4.0 * g2);
-          const double u = (d >= 0.0 ? 2.0 : -2.0) / (fabs(d) + h);
-          c = rsqrt(1.0 + u * u * g2);
-          sg = rmul(c * u, g);   // sigma = s * gamma/|gamma|
+          const double rh = rsqrt(d * d + 4.0 * g2);
+          const double x = 0.5 * (1.0 + fabs(d) * rh);
+          const double rx = rsqrt(x);
+          c = x * rx;
+          sg = rmul(d >= 0.0 ? rh * rx : -(rh * rx), g);
         }
-        s_rc[lane] = c; s_rs[lane] = sg; s_rp[lane] = p; s_rq[lane] = q;
+        s_rc[tid] = c; s_rs[tid] = sg; s_rp[tid] = p; s_rq[tid] = q;
       }
-      const unsigned any = __ballot_sync(0xffffffffu, rot);
-      if (!any) continue;
-      __syncwarp();
-      // W <- J^H W J   (J_a = [[c, s],[-conj(s), c]] on columns (p,q) of pair a)
-#pragma unroll
-      for (int b2 = 0; b2 < 2; ++b2) {
-        const int blk = lane + 32 * b2;
-        const int ia = blk >> 3, ib = blk & 7;
+      if (!__syncthreads_or(rot)) continue;
+      if (warp < 2) {
+        // W <- J^H W J   (J_a = [[c, s],[-conj(s), c]] on columns (p,q) of pair a); one 2x2 block pair per thread
+        const int ia = tid >> 3, ib = tid & 7;
         const int pa = s_rp[ia], qa = s_rq[ia], pb = s_rp[ib], qb = s_rq[ib];
         const double ca = s_rc[ia], cb = s_rc[ib];
         const double2 sa = s_rs[ia], sb = s_rs[ib];
@@ -196,23 +216,25 @@ __global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem*
         sW[pa * WLD + qb] = cadd(cmul(sb, t00), rmul(cb, t01));
         sW[qa * WLD + pb] = csub(rmul(cb, t10), cmulc(sb, t11));
         sW[qa * WLD + qb] = cadd(cmul(sb, t10), rmul(cb, t11));
-      }
-      // Q <- Q J
+      } else {
+        // Q <- Q J
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int it = lane + 32 * k;
-        const int row = it >> 3, ia = it & 7;
-        const int pa = s_rp[ia], qa = s_rq[ia];
-        const double ca = s_rc[ia];
-        const double2 sa = s_rs[ia];
-        const double2 x = sQ[row * WLD + pa], y = sQ[row * WLD + qa];
-        sQ[row * WLD + pa] = csub(rmul(ca, x), cmulc(sa, y));
-        sQ[row * WLD + qa] = cadd(cmul(sa, x), rmul(ca, y));
+        for (int k = 0; k < 2; ++k) {
+          const int it = (tid - 64) + 64 * k;
+          const int row = it >> 3, ia = it & 7;
+          const int pa = s_rp[ia], qa = s_rq[ia];
+          const double ca = s_rc[ia];
+          const double2 sa = s_rs[ia];
+          const double2 x = sQ[row * WLD + pa], y = sQ[row * WLD + qa];
+          sQ[row * WLD + pa] = csub(rmul(ca, x), cmulc(sa, y));
+          sQ[row * WLD + qa] = cadd(cmul(sa, x), rmul(ca, y));
+        }
       }
-      __syncwarp();
+      __syncthreads();
     }
   }
   __syncthreads();
+  if (timing) { tD = clock64(); atomicAdd(&g_phase_cycles[2], (unsigned long long)(tD - tC)); }
 
   // ------------------------------------------------------------------ phase C: X <- X Q on DMMA, in place
   {
@@ -243,7 +265,7 @@ __global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem*
       for (int u = 0; u < UN; ++u) {
         const int row = 8 * (base + u) + (lane >> 2);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) xa[u][k4] = (row < M && src[k4]) ? src[k4][row] : make_double2(0.0, 0.0);
+        for (int k4 = 0; k4 < 4; ++k4) xa[u][k4] = (row < M && src[k4]) ? __ldcg(src[k4] + row) : make_double2(0.0, 0.0);
       }
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
@@ -268,6 +290,88 @@ __global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem*
               if (dst[jn][e]) dst[jn][e][row] = make_double2(re[jn][e], im[jn][e]);
         }
       }
+    }
+  }
+  if (timing) { atomicAdd(&g_phase_cycles[3], (unsigned long long)(clock64() - tD)); atomicAdd(&g_phase_cycles[6], 1ull); }
+}
+
+// One step of the tournament for the whole batch (grid = pairs x matrices); kept for A/B runs (option "jacobi_persistent" 0).
+__global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem* __restrict__ probs, int step, double tol2, double dead2,
+                                                            const double* __restrict__ fro2, int* __restrict__ dirty,
+                                                            const int* __restrict__ done) {
+  const int mat = blockIdx.y;
+  if (done[mat]) return;
+  const JacobiProblem P = probs[mat];
+  const int npairs = (P.nb == 1) ? 1 : P.nbe / 2;
+  if ((int)blockIdx.x >= npairs) return;
+  int blkA, blkB;
+  bool within;
+  if (!pair_blocks(P, step, blockIdx.x, blkA, blkB, within)) return;
+  pair_task(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// A whole sweep (nsteps tournament steps) of the whole batch in ONE launch: persistent CTAs pull pair tasks from a global
+// counter in (step, matrix, pair) order and wait on per-block progress flags instead of on a kernel boundary:
+//   task (s, m, A, B) may start when progress[m][A] >= base + s and progress[m][B] >= base + s, and publishes base + s + 1.
+// Tasks are dequeued in dependency order and a waiting CTA only waits on tasks dequeued before its own, which are
+// finished or running on resident CTAs, so the scheme cannot deadlock.  Compared with one launch per step this removes
+// ~60 launch boundaries per sweep and lets the Gram / rotate / apply phases of different pairs overlap on an SM.
+__global__ void __launch_bounds__(JT, 4) jacobi_sweep_kernel(const JacobiProblem* __restrict__ probs, int batch, int max_pairs, int nsteps,
+                                                             int base, double tol2, double dead2, const double* __restrict__ fro2,
+                                                             int* __restrict__ dirty, const int* __restrict__ done,
+                                                             int* __restrict__ progress, int progress_stride, int* __restrict__ counter,
+                                                             int* __restrict__ fault, int stagger_ns) {
+  __shared__ int s_task;
+  const int per_step = batch * max_pairs;
+  const int total = nsteps * per_step;
+  for (;;) {
+    if (threadIdx.x == 0) s_task = atomicAdd(counter, 1);
+    __syncthreads();
+    const int t = s_task;
+    __syncthreads();   // s_task may be overwritten from here on
+    if (t >= total) return;
+    const int step = t / per_step, r = t - step * per_step;
+    const int mat = r / max_pairs, pi = r - mat * max_pairs;
+    if (done[mat]) continue;
+    const JacobiProblem P = probs[mat];
+    const int npairs = (P.nb == 1) ? 1 : P.nbe / 2;
+    if (pi >= npairs) continue;
+    int blkA, blkB;
+    bool within;
+    if (!pair_blocks(P, step, pi, blkA, blkB, within)) continue;
+    int* prog = progress + (size_t)mat * progress_stride;
+    long long tw = 0;
+    if (threadIdx.x == 0 && g_dbg_mode == 10) tw = clock64();
+    if (threadIdx.x == 0) {
+      // Every block of a matrix takes part in every step, so the tasks of one matrix move in lockstep and the DMMA pipe
+      // idles while they are all in the serial rotation phase.  Delaying every other matrix by part of a step at the
+      // start of the sweep puts the matrices out of phase with each other.
+      if (step == 0 && (mat & 1) && stagger_ns > 0) {
+        for (int w = 0; w < stagger_ns; w += 1000) __nanosleep(1000);
+      }
+      // bounded wait (~1 s): a scheduling bug must surface as an error on the host, never as a hung GPU
+      const int need = base + step;
+      unsigned spins = 0;
+      while (ld_acquire(prog + blkA) < need && ++spins < (1u << 23)) __nanosleep(64);
+      if (blkB >= 0)
+        while (ld_acquire(prog + blkB) < need && ++spins < (1u << 23)) __nanosleep(64);
+      if (spins >= (1u << 23)) atomicAdd(fault, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && g_dbg_mode == 10) atomicAdd(&g_phase_cycles[4], (unsigned long long)(clock64() - tw));
+    pair_task(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      st_release(prog + blkA, base + step + 1);
+      if (blkB >= 0) st_release(prog + blkB, base + step + 1);
     }
   }
 }
@@ -394,6 +498,23 @@ void launch_jacobi_step(const JacobiProblem* d_probs, int batch, int max_pairs, 
   if (batch <= 0) return;
   dim3 grid(max_pairs, batch);
   jacobi_step_kernel<<<grid, JT, 0, s>>>(d_probs, step, tol2, dead2, d_fro2, d_dirty, d_done);
+}
+void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
+                         const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
+                         int* d_fault, int grid_ctas, int stagger_ns, cudaStream_t s) {
+  if (batch <= 0) return;
+  const long total = (long)nsteps * batch * max_pairs;
+  const int grid = (int)std::min<long>(total, grid_ctas);
+  jacobi_sweep_kernel<<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done, d_progress,
+                                          progress_stride, d_counter, d_fault, stagger_ns);
+}
+void jacobi_set_debug_mode(int mode) { cudaMemcpyToSymbol(g_dbg_mode, &mode, sizeof(int)); }
+void jacobi_print_phase_timing() {
+  unsigned long long h[8];
+  if (cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof(h)) != cudaSuccess || h[5] == 0) return;
+  const double n = (double)h[5], nr = (double)(h[6] ? h[6] : 1);
+  fprintf(stderr, "[mps_b200 phase timing] tasks %.0f (rotating %.0f): A %.0f cyc, reduce+test %.0f, B %.0f (per rotating), C %.0f (per rotating), dep-wait %.0f\n",
+          n, (double)h[6], h[0] / n, h[1] / n, h[2] / nr, h[3] / nr, h[4] / n);
 }
 void launch_fro2(const JacobiProblem* d_probs, int batch, double* d_fro2, cudaStream_t s) {
   if (batch <= 0) return;

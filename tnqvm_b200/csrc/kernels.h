@@ -58,6 +58,13 @@ struct JacobiProblem {
 };
 void launch_jacobi_step(const JacobiProblem* d_probs, int batch, int max_pairs, int step, double tol2, double dead2,
                         const double* d_fro2, int* d_dirty, const int* d_done, cudaStream_t s);
+// one whole sweep (nsteps steps) in one persistent launch; d_progress: per matrix `progress_stride` ints (>= nbe), zeroed once
+// per SVD; base = steps completed by the previous sweeps; *d_counter zeroed (one counter per launch)
+void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
+                         const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
+                         int* d_fault, int grid_ctas, int stagger_ns, cudaStream_t s);   // *d_fault += 1 if a dependency wait timed out
+void jacobi_set_debug_mode(int mode);   // timing experiments only
+void jacobi_print_phase_timing();
 void launch_fro2(const JacobiProblem* d_probs, int batch, double* d_fro2, cudaStream_t s);   // d_fro2 pre-zeroed
 // after a sweep: done[m] |= !dirty[m]; dirty[m] = 0; *remaining = #not done
 void launch_jacobi_check(int batch, int* d_dirty, int* d_done, int* d_remaining, cudaStream_t s);
