@@ -94,6 +94,10 @@ struct mps_b200_handle {
   std::mt19937_64 rng;
   double discarded = 0.0;
   std::string err;
+  // <psi|psi> of a register is remembered until its state changes (expval_z_all computes it on the way)
+  uint64_t state_ver = 1;
+  std::vector<uint64_t> norm_ver;
+  std::vector<double> norm_val;
   // device workspace
   Arena ws;
   // pinned staging: two regions (pre-sync / post-sync uploads), plus read-back area
@@ -109,6 +113,7 @@ struct mps_b200_handle {
   int jacobi_persistent = 1;   // one persistent dataflow launch per sweep (jacobi_sweep_kernel) instead of one launch per step
   int sm_count = 148;
   int stagger_ns = 0;
+  double discard_margin = 0.0;    // discard-aware rotation rule: fraction of the keep-th largest squared column norm (0 = off)
   cudaStream_t gstream[NGROUP] = {};
   cudaEvent_t gev[NGROUP][GDEPTH] = {};
   cudaEvent_t gend[NGROUP] = {}, gstart = nullptr;
@@ -170,6 +175,7 @@ struct mps_b200_handle {
   // ------------------------------------------------------------------ state
   void reset_state() {
     CK(cudaStreamSynchronize(stream));
+    ++state_ver;
     queue.clear();
     std::fill(has1q.begin(), has1q.end(), 0);
     measure.clear();
@@ -234,6 +240,7 @@ struct mps_b200_handle {
   }
 
   void flush() {
+    if (!queue.empty() || std::find(has1q.begin(), has1q.end(), (char)1) != has1q.end()) ++state_ver;
     if (!queue.empty()) {
       // dependency layering: a gate goes one layer after the last gate touching any of its sites
       std::vector<int> level(ntot, -1);
@@ -309,7 +316,7 @@ struct mps_b200_handle {
     nlayers += 1;
     n2q += B;
 
-    struct Dim { int lo, cl, ch, cr, M, N, tall, Mg, Ng, Mj; size_t oT, oG, oY, oV, oTq, oSig2, oSigma, oPerm, oSP, oSO, oKeep, oW; };
+    struct Dim { int lo, cl, ch, cr, M, N, tall, Mg, Ng, Mj; size_t oT, oG, oY, oV, oTq, oCn2, oSig2, oSigma, oPerm, oSP, oSO, oKeep, oW; };
     std::vector<Dim> D(B);
     ws.reset();
     // pass 1: sizes
@@ -334,6 +341,7 @@ struct mps_b200_handle {
     int pstride = 2;   // progress flags per matrix of the persistent sweep kernel: one per 8-column block
     for (int b = 0; b < B; ++b) pstride = std::max(pstride, ((D[b].Ng + 7) / 8 + 1) & ~1);
     const size_t oProg = ws.reserve(sizeof(int) * ((size_t)B * pstride + max_sweeps + 4));
+    const size_t oThr = ws.reserve(sizeof(double) * B);   // discard-aware thresholds, zero = off (inside the zeroed block)
     const size_t oFlags = ws.reserve(sizeof(int) * (2 * B + 4) + sizeof(double) * B + 16);   // dirty[B], done[B], remaining, pad, fro2[B]
     const size_t oKeepBlk = ws.reserve((sizeof(int) + 2 * sizeof(double)) * B + 64);
     size_t sig_total = 0;
@@ -351,6 +359,7 @@ struct mps_b200_handle {
     }
     for (int b = 0; b < B; ++b) {
       Dim& d = D[b];
+      d.oCn2 = ws.reserve(sizeof(double) * d.Ng);
       d.oSig2 = ws.reserve(sizeof(double) * d.Ng);
       d.oPerm = ws.reserve(sizeof(int) * d.Ng);
       d.oSP = ws.reserve(sizeof(double) * d.Ng);
@@ -404,6 +413,7 @@ struct mps_b200_handle {
       }
       j.nb = (d.Ng + 7) / 8;
       j.nbe = (j.nb == 1) ? 1 : ((j.nb + 1) & ~1);
+      j.cn2 = (double*)(wb + d.oCn2); j.thr = (double*)(wb + oThr) + b;
       max_pairs = std::max(max_pairs, j.nb == 1 ? 1 : j.nbe / 2);
       max_steps = std::max(max_steps, j.nb == 1 ? 1 : j.nbe - 1);
       maxMg = std::max(maxMg, d.Mg);
@@ -454,6 +464,10 @@ struct mps_b200_handle {
                             d_done, d_prog, pstride, d_cnt + sweep, d_rem + 1, sm_count * 4, stagger_ns, stream);
         launch_jacobi_check(B, d_dirty, d_done, d_rem, stream);
         nlaunch += 2;
+        if (discard_margin > 0 && maxNg > max_bond) {
+          launch_jacobi_thr((const JacobiProblem*)(wb + oJac), B, max_bond, discard_margin, d_done, stream);
+          nlaunch += 1;
+        }
         CK(cudaMemcpyAsync(h_rem, d_rem, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
         if (trace) CK(cudaEventRecord(ev[3], stream));
         CK(cudaStreamSynchronize(stream));
@@ -618,6 +632,15 @@ struct mps_b200_handle {
 
   void left_step(const SiteBuf& S, const double2* E, double2* F, double2* Eout, double w0, double w1) {
     const int dl = S.dl, dr = S.dr;
+    if (w0 == w1) {
+      // both physical slices in one GEMM: the site is a column-major dl x (2 dr) matrix with column index p + 2c
+      GemmProblem g;
+      memset(&g, 0, sizeof(g));
+      g.A = E; g.lda = dl; g.B = S.d; g.ldb = dl; g.C = F; g.ldc = dl;
+      g.M = dl; g.N = 2 * dr; g.K = dl; g.b_col_stride = 1; g.alpha = w0;
+      launch_gemm1(g, 0, stream);
+      nlaunch += 1;
+    } else
     for (int p = 0; p < 2; ++p) {
       GemmProblem g;
       memset(&g, 0, sizeof(g));
@@ -630,16 +653,17 @@ struct mps_b200_handle {
     g.A = S.d; g.lda = 2 * dl; g.B = F; g.ldb = 2 * dl; g.C = Eout; g.ldc = dr;
     g.M = dr; g.N = dr; g.K = 2 * dl; g.b_col_stride = 1; g.alpha = 1.0;
     launch_gemm1(g, 1, stream);
-    nlaunch += 3;
+    nlaunch += (w0 == w1) ? 1 : 3;
   }
   // R_k[a,a'] = sum_{p,c,c'} A[a,p,c] R[c,c'] conj(A[a',p,c'])
   void right_step(const SiteBuf& S, const double2* R, double2* H, double2* Rout) {
     const int dl = S.dl, dr = S.dr;
-    for (int p = 0; p < 2; ++p) {
+    {
+      // H[(a,p), c'] = sum_c S[(a,p), c] R[c, c']: the site as a (2 dl) x dr matrix, both physical slices in one GEMM
       GemmProblem g;
       memset(&g, 0, sizeof(g));
-      g.A = S.d + (size_t)p * dl; g.lda = 2 * dl; g.B = R; g.ldb = dr; g.C = H + (size_t)p * dl; g.ldc = 2 * dl;
-      g.M = dl; g.N = dr; g.K = dr; g.b_col_stride = 1; g.alpha = 1.0;
+      g.A = S.d; g.lda = 2 * dl; g.B = R; g.ldb = dr; g.C = H; g.ldc = 2 * dl;
+      g.M = 2 * dl; g.N = dr; g.K = dr; g.b_col_stride = 1; g.alpha = 1.0;
       launch_gemm1(g, 0, stream);
     }
     GemmProblem g;
@@ -647,7 +671,7 @@ struct mps_b200_handle {
     g.A = H; g.lda = dl; g.B = S.d; g.ldb = dl; g.C = Rout; g.ldc = dl;
     g.M = dl; g.N = dl; g.K = 2 * dr; g.b_col_stride = 1; g.alpha = 1.0;
     launch_gemm1(g, 2, stream);
-    nlaunch += 3;
+    nlaunch += 2;
   }
 
   size_t max_env_elems(int s0, int s1) const {
@@ -713,21 +737,50 @@ struct mps_b200_handle {
     for (int k = n - 1; k >= 0; --k) right_step(sites[s0 + k], Rv[k + 1], F, Rv[k]);
   }
 
+  // <Z_k> for every k and the norm from ONE left and ONE right transfer sweep: the left sweep keeps F_k = L_k S_k, the
+  // right sweep forms H_k = S_k R_{k+1}, and <psi| Z_k |psi> = sum_{a,p,c} (-1)^p conj(F_k[a,p,c]) H_k[a,p,c]
+  // (L_k is Hermitian).  4 GEMMs + one reduction per site instead of 9 GEMMs.
   void expval_z_all(int reg, double* out) {
-    std::vector<double2*> Lv, Rv;
-    double2 *F, *Et, *Et2, *scal;
-    build_envs(reg, Lv, Rv, F, Et, Et2, scal);
-    const int s0 = reg * nq;
-    for (int k = 0; k < nq; ++k) {
-      left_step(sites[s0 + k], Lv[k], F, Et, 1.0, -1.0);
-      launch_trace_pair(Et, Rv[k + 1], sites[s0 + k].dr, scal + k, stream);
-      nlaunch += 1;
+    flush();
+    const int s0 = reg * nq, n = nq;
+    ws.reset();
+    std::vector<size_t> oF(n);
+    size_t maxL = 1;
+    for (int k = 0; k < n; ++k) {
+      oF[k] = ws.reserve((size_t)2 * sites[s0 + k].dl * sites[s0 + k].dr * 16);
+      maxL = std::max(maxL, (size_t)sites[s0 + k].dr * sites[s0 + k].dr);
     }
-    std::vector<cplx> h(nq);
-    CK(cudaMemcpyAsync(h.data(), scal, 16 * (size_t)nq, cudaMemcpyDeviceToHost, stream));
+    const size_t oE0 = ws.reserve(maxL * 16), oE1 = ws.reserve(maxL * 16);
+    const size_t oH = ws.reserve(max_site_elems(s0, s0 + n) * 16);
+    const size_t oS = ws.reserve(16 * (size_t)(n + 8));
+    ensure_ws(ws.off);
+    double2* E[2] = {(double2*)(ws.base + oE0), (double2*)(ws.base + oE1)};
+    double2* H = (double2*)(ws.base + oH);
+    double2* scal = (double2*)(ws.base + oS);
+    const cplx one(1, 0);
+    CK(cudaMemcpyAsync(E[0], &one, 16, cudaMemcpyHostToDevice, stream));
+    int cur = 0;
+    for (int k = 0; k < n; ++k) {
+      left_step(sites[s0 + k], E[cur], (double2*)(ws.base + oF[k]), E[cur ^ 1], 1.0, 1.0);
+      cur ^= 1;
+    }
+    CK(cudaMemcpyAsync(scal + n, E[cur], 16, cudaMemcpyDeviceToDevice, stream));   // <psi|psi>
+    CK(cudaMemcpyAsync(E[0], &one, 16, cudaMemcpyHostToDevice, stream));
+    cur = 0;
+    for (int k = n - 1; k >= 0; --k) {
+      const SiteBuf& S = sites[s0 + k];
+      right_step(S, E[cur], H, E[cur ^ 1]);
+      launch_site_dot((const double2*)(ws.base + oF[k]), H, S.dl, S.dr, 1.0, -1.0, scal + k, stream);
+      nlaunch += 1;
+      cur ^= 1;
+    }
+    std::vector<cplx> h(n + 1);
+    CK(cudaMemcpyAsync(h.data(), scal, 16 * (size_t)(n + 1), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
-    for (int k = 0; k < nq; ++k) out[k] = h[k].real();
+    for (int k = 0; k < n; ++k) out[k] = h[k].real();
+    norm_val[reg] = h[n].real();
+    norm_ver[reg] = state_ver;
   }
 
   void expval_zz_pairs(int reg, int np, const int* qi, const int* qj, double* out) {
@@ -847,6 +900,8 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     CK(cudaEventCreateWithFlags(&h->gstart, cudaEventDisableTiming));
     CK(cudaMallocHost(&h->pin_rem, sizeof(int) * mps_b200_handle::NGROUP * mps_b200_handle::GDEPTH));
     h->sites.resize(h->ntot);
+    h->norm_ver.assign(h->nreg, 0);
+    h->norm_val.assign(h->nreg, 0.0);
     h->has1q.assign(h->ntot, 0);
     h->p1q.resize(h->ntot);
     h->sv.assign(std::max(h->ntot - 1, 1), std::vector<double>{1.0});
@@ -856,9 +911,11 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     if (const char* e = getenv("MPS_B200_PERSISTENT")) h->jacobi_persistent = atoi(e) != 0;
     if (const char* e = getenv("MPS_B200_MAX_SWEEPS")) h->max_sweeps = std::max(1, atoi(e));
     if (const char* e = getenv("MPS_B200_STAGGER_NS")) h->stagger_ns = atoi(e);
+    if (const char* e = getenv("MPS_B200_DISCARD_MARGIN")) h->discard_margin = atof(e);
     if (const char* e = getenv("MPS_B200_DBG_MODE")) jacobi_set_debug_mode(atoi(e));
     h->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("MPS_B200_JACOBI_TOL")) h->jacobi_tol = atof(e);
+    if (const char* e = getenv("MPS_B200_NULL_TOL")) h->null_tol = atof(e);
     if (seed) h->rng.seed(seed);
     else { std::random_device rd; h->rng.seed(rd()); }   // RandomEngine.hpp:39-42
     h->reset_state();
@@ -911,6 +968,7 @@ int mps_set_option(mps_handle_t h, const char* key, double value) {
   else if (k == "qr_prereduce") { h->flush(); h->use_qr = value != 0; }
   else if (k == "jacobi_groups") { h->flush(); h->jacobi_groups = std::max(1, (int)value); }
   else if (k == "jacobi_persistent") { h->flush(); h->jacobi_persistent = value != 0; }
+  else if (k == "discard_margin") { h->flush(); h->discard_margin = value; }
   else if (k == "max_bond") h->max_bond = value > 0 ? (int)value : INT_MAX - 1;
   else if (k == "svd_cutoff") h->cutoff = value >= 0 ? value : DBL_MIN;
   else if (k == "gauge") h->gauge = (int)value;
@@ -940,8 +998,13 @@ int mps_sync(mps_handle_t h) {
 int mps_norm(mps_handle_t h, int reg, double* out) {
   API_BEGIN(h)
   if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
-  std::vector<std::array<double, 2>> w(h->nq, {1.0, 1.0});
-  *out = h->sweep_weights(reg, w).real();
+  h->flush();
+  if (h->norm_ver[reg] != h->state_ver) {
+    std::vector<std::array<double, 2>> w(h->nq, {1.0, 1.0});
+    h->norm_val[reg] = h->sweep_weights(reg, w).real();
+    h->norm_ver[reg] = h->state_ver;
+  }
+  *out = h->norm_val[reg];
   API_END(h)
 }
 int mps_expval_z(mps_handle_t h, int reg, int nq, const int* qubits, double* out) {
@@ -1093,6 +1156,7 @@ int mps_get_site(mps_handle_t h, int k, double* out, int shape[3]) {
 int mps_set_site(mps_handle_t h, int k, const double* in, int dl, int dr) {
   API_BEGIN(h)
   h->flush();
+  ++h->state_ver;   // the caller may change the tensor
   if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
   h->ensure_site(k, dl, dr, false);
   CK(cudaMemcpyAsync(h->sites[k].d, in, (size_t)2 * dl * dr * 16, cudaMemcpyHostToDevice, h->stream));
@@ -1102,6 +1166,7 @@ int mps_set_site(mps_handle_t h, int k, const double* in, int dl, int dr) {
 int mps_site_device_ptr(mps_handle_t h, int k, void** dptr, int shape[3]) {
   API_BEGIN(h)
   h->flush();
+  ++h->state_ver;   // the caller may change the tensor
   CK(cudaStreamSynchronize(h->stream));
   if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
   const SiteBuf& s = h->sites[k];
@@ -1112,6 +1177,7 @@ int mps_site_device_ptr(mps_handle_t h, int k, void** dptr, int shape[3]) {
 int mps_resize_site(mps_handle_t h, int k, int dl, int dr, void** dptr) {
   API_BEGIN(h)
   h->flush();
+  ++h->state_ver;   // the caller may change the tensor
   if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
   h->ensure_site(k, dl, dr, false);
   CK(cudaStreamSynchronize(h->stream));

@@ -61,6 +61,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   // columns whose squared norm is below dead_abs (<= (null_tol * sigma_max)^2) are numerically null: they are zeroed at
   // write-back and never rotated, so rank-deficient thetas do not spend sweeps orthogonalising rounding noise
   const double dead_abs = dead2 * fro2[mat] / (double)N;
+  const double thr = *P.thr;   // both columns below thr: both will be truncated, leave the pair alone
 
   __shared__ int s_cols[16];
   __shared__ double s_red[4][7][64];
@@ -80,6 +81,16 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   }
   if (tid == 0) s_need = 0;
   __syncthreads();
+  if (thr > 0.0) {
+    // all 16 columns already below the threshold: nothing this task could rotate, skip even the Gram matrix
+    if (tid < 16 && s_cols[tid] >= 0 && __ldcg(P.cn2 + s_cols[tid]) >= thr) s_need = 1;
+    __syncthreads();
+    const int any = s_need;
+    __syncthreads();
+    if (!any) return;
+    if (tid == 0) s_need = 0;
+    __syncthreads();
+  }
   const bool timing = (g_dbg_mode == 10) && tid == 0;
   long long tA = 0, tB = 0, tC = 0, tD = 0;
   if (timing) tA = clock64();
@@ -153,14 +164,17 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
       if (p < q && (within || (p < 8 && q >= 8))) {   // pairs inside a block belong to the first step of the tournament
         const double a = sW[p * WLD + p].x, b = sW[q * WLD + q].x;
         const double2 g = sW[p * WLD + q];
-        if (a > dead_abs && b > dead_abs && (g.x * g.x + g.y * g.y) > tol2 * a * b) need = 1;
+        if (a > dead_abs && b > dead_abs && (a >= thr || b >= thr) && (g.x * g.x + g.y * g.y) > tol2 * a * b) need = 1;
       }
     }
     if (need) s_need = 1;   // benign race: all writers store 1
   }
   __syncthreads();
   if (timing) { tC = clock64(); atomicAdd(&g_phase_cycles[0], (unsigned long long)(tB - tA)); atomicAdd(&g_phase_cycles[1], (unsigned long long)(tC - tB)); atomicAdd(&g_phase_cycles[5], 1ull); }
-  if (!s_need) return;
+  if (!s_need) {
+    if (tid < 16 && s_cols[tid] >= 0) P.cn2[s_cols[tid]] = sW[tid * WLD + tid].x;
+    return;
+  }
   if (tid == 0) dirty[mat] = 1;
 
   // ------------------------------------------------------------------ phase B: Jacobi rotations on W (all four warps)
@@ -187,7 +201,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
         const double g2 = g.x * g.x + g.y * g.y;
         double c = 1.0;
         double2 sg = make_double2(0.0, 0.0);
-        if (a > dead_abs && b > dead_abs && g2 > tol2 * a * b) {
+        if (a > dead_abs && b > dead_abs && (a >= thr || b >= thr) && g2 > tol2 * a * b) {
           rot = 1;
           // cos 2t = |d|/h, sin 2t = 2|g|/h  (|t| <= pi/4):  c = sqrt((1 + |d|/h)/2),  s = sign(d) g / (h c)
           const double d = b - a;
@@ -233,6 +247,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
       __syncthreads();
     }
   }
+  if (tid < 16 && s_cols[tid] >= 0) P.cn2[s_cols[tid]] = sW[tid * WLD + tid].x;   // the last round ended with a barrier
   __syncthreads();
   if (timing) { tD = clock64(); atomicAdd(&g_phase_cycles[2], (unsigned long long)(tD - tC)); }
 
@@ -395,6 +410,26 @@ __global__ void __launch_bounds__(256) fro2_kernel(const JacobiProblem* __restri
   if (threadIdx.x == 0 && sh[0] != 0.0) atomicAdd(fro2 + blockIdx.y, sh[0]);
 }
 
+__global__ void __launch_bounds__(256) jacobi_thr_kernel(const JacobiProblem* __restrict__ probs, int keep, double margin,
+                                                         const int* __restrict__ done) {
+  const int mat = blockIdx.x;
+  if (done[mat]) return;
+  const JacobiProblem P = probs[mat];
+  if (P.N <= keep) return;   // nothing will be truncated by max-bond-dim: rule stays off
+  extern __shared__ double s_cn[];
+  for (int i = threadIdx.x; i < P.N; i += 256) s_cn[i] = P.cn2[i];
+  __syncthreads();
+  for (int k = threadIdx.x; k < P.N; k += 256) {
+    const double v = s_cn[k];
+    int rank = 0;
+    for (int j = 0; j < P.N; ++j) {
+      const double w = s_cn[j];
+      rank += (w > v || (w == v && j < k)) ? 1 : 0;
+    }
+    if (rank == keep - 1) *P.thr = margin * v;
+  }
+}
+
 __global__ void jacobi_check_kernel(int batch, int* dirty, int* done, int* remaining) {
   __shared__ int cnt;
   if (threadIdx.x == 0) cnt = 0;
@@ -507,6 +542,10 @@ void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs,
   const int grid = (int)std::min<long>(total, grid_ctas);
   jacobi_sweep_kernel<<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done, d_progress,
                                           progress_stride, d_counter, d_fault, stagger_ns);
+}
+void launch_jacobi_thr(const JacobiProblem* d_probs, int batch, int keep, double margin, const int* d_done, cudaStream_t s) {
+  if (batch <= 0 || keep <= 0 || margin <= 0.0) return;
+  jacobi_thr_kernel<<<batch, 256, 48 * 1024, s>>>(d_probs, keep, margin, d_done);
 }
 void jacobi_set_debug_mode(int mode) { cudaMemcpyToSymbol(g_dbg_mode, &mode, sizeof(int)); }
 void jacobi_print_phase_timing() {

@@ -55,7 +55,14 @@ struct JacobiProblem {
   int M, N, ldg;
   int nb;    // column blocks of 8 (ceil(N/8))
   int nbe;   // nb rounded up to even (>= 2) ; 1 when nb == 1
+  // discard-aware rotation rule: cn2[N] = current squared column norms (written by the pair tasks); *thr = a fraction of
+  // the keep-th largest of them (jacobi_thr_kernel, once per sweep; 0 = rule off).  Two columns that are both below
+  // *thr are both certain to be truncated and need not be orthogonalised against each other.
+  double* cn2;
+  double* thr;
 };
+// per sweep: *thr = margin * (keep-th largest cn2) for every matrix with N > keep that is still rotating
+void launch_jacobi_thr(const JacobiProblem* d_probs, int batch, int keep, double margin, const int* d_done, cudaStream_t s);
 void launch_jacobi_step(const JacobiProblem* d_probs, int batch, int max_pairs, int step, double tol2, double dead2,
                         const double* d_fro2, int* d_dirty, const int* d_done, cudaStream_t s);
 // one whole sweep (nsteps steps) in one persistent launch; d_progress: per matrix `progress_stride` ints (>= nbe), zeroed once
@@ -107,6 +114,8 @@ void launch_gate1q(const Gate1qProblem* d_probs, int batch, long max_elems, cuda
 
 // out[0] = sum_{i,j} E[i + n*j] * R[j + n*i]   (trace(E R)), complex
 void launch_trace_pair(const double2* E, const double2* R, int n, double2* out, cudaStream_t s);
+// out[0] = sum_{a,p,c} w_p conj(F[a,p,c]) H[a,p,c]  (site-shaped arrays (dl,2,dr), column-major)
+void launch_site_dot(const double2* F, const double2* H, int dl, int dr, double w0, double w1, double2* out, cudaStream_t s);
 void launch_fill(double2* p, long n, double2 v, cudaStream_t s);
 void launch_randn(double2* p, long n, uint64_t seed, cudaStream_t s);
 

@@ -50,6 +50,29 @@ __global__ void __launch_bounds__(256) trace_pair_kernel(const double2* __restri
   if (threadIdx.x == 0) *out = make_double2(sr[0], si[0]);
 }
 
+// out = sum_{a,p,c} w_p conj(F[a,p,c]) H[a,p,c]  over a site-shaped pair (dl, 2, dr); single CTA, fixed reduction order.
+// With F_p = L S_p (left sweep) and H_p = S_p R (right sweep) and Hermitian L this is <psi| diag(w0, w1)_k |psi>.
+__global__ void __launch_bounds__(1024) site_dot_kernel(const double2* __restrict__ F, const double2* __restrict__ H, int dl, int dr,
+                                                        double w0, double w1, double2* __restrict__ out) {
+  double re = 0.0, im = 0.0;
+  const long total = 2L * dl * dr;
+  for (long e = threadIdx.x; e < total; e += 1024) {
+    const int p = (int)((e / dl) & 1);
+    const double w = p ? w1 : w0;
+    const double2 a = F[e], b = H[e];
+    re += w * (a.x * b.x + a.y * b.y);
+    im += w * (a.x * b.y - a.y * b.x);
+  }
+  __shared__ double sr[1024], si[1024];
+  sr[threadIdx.x] = re; si[threadIdx.x] = im;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sr[threadIdx.x] += sr[threadIdx.x + o]; si[threadIdx.x] += si[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = make_double2(sr[0], si[0]);
+}
+
 __global__ void fill_kernel(double2* p, long n, double2 v) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -81,6 +104,9 @@ void launch_gate1q(const Gate1qProblem* d_probs, int batch, long max_elems, cuda
 }
 void launch_trace_pair(const double2* E, const double2* R, int n, double2* out, cudaStream_t s) {
   trace_pair_kernel<<<1, 256, 0, s>>>(E, R, n, out);
+}
+void launch_site_dot(const double2* F, const double2* H, int dl, int dr, double w0, double w1, double2* out, cudaStream_t s) {
+  site_dot_kernel<<<1, 1024, 0, s>>>(F, H, dl, dr, w0, w1, out);
 }
 void launch_fill(double2* p, long n, double2 v, cudaStream_t s) {
   if (n <= 0) return;
