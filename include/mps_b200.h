@@ -95,7 +95,7 @@ int mps_resize_site(mps_handle_t h, int k, int dl, int dr, void** dptr);
 
 /* counters: [0] 2q gates executed, [1] 1q kernel gates, [2] layers, [3] jacobi sweeps, [4] kernel launches,
  * [5] ms merge GEMM, [6] ms SVD (QR pre-reduction + Jacobi), [7] ms truncate+write-back, [8] ms of [6] spent in the QR
- * pre-reduction (5..8 only with option "profile") */
+ * pre-reduction (5..8 only with option "profile"), [9] real flops issued on the DMMA pipe by the Jacobi pair tasks (process-wide) */
 int mps_stats(mps_handle_t h, double* out, int cap);
 /* the CUDA stream (cudaStream_t) all work of this handle is issued on: callers time with events recorded on it
  * and order their own transfers (NCCL send/recv of boundary sites) against it */

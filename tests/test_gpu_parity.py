@@ -104,6 +104,46 @@ def test_golden_fixtures_on_gpu():
         e.close()
 
 
+@pytest.mark.parametrize("opts", [dict(qr_prereduce=0), dict(jacobi_persistent=0), dict(jacobi_persistent=0, jacobi_groups=3),
+                                  dict(qr_prereduce=0, jacobi_persistent=0), dict(discard_margin=1e-12)],
+                         ids=["no_qr", "step_kernels", "stream_groups", "no_qr_step_kernels", "discard_rule"])
+def test_svd_engine_variants_agree_with_oracle(O, opts):
+    """Every SVD configuration (QR pre-reduction on/off, persistent dataflow sweep vs one launch per step, stream groups,
+    discard-aware rule) must give the reference's observables: exact run at 1e-10, truncated run at TRUNC_TOL."""
+    n = 14
+    circ = Cc.brickwork(n, 10, seed=21, prefix_ghz=True)
+    for chi, tol in ((0, EXACT_TOL), (16, TRUNC_TOL)):
+        e = gpu_run(n, circ, max_bond=chi, **opts)
+        o = O.OracleMPS(n, max_bond=chi).run(circ)
+        zo = np.array([o.expval_z([k]) for k in range(n)])
+        assert np.abs(e.expval_z_all() - zo).max() < tol, (opts, chi)
+        assert abs(e.norm() - o.norm()) < tol, (opts, chi)   # served from the cache expval_z_all filled
+        e.set_option("fuse_1q", 1)                           # any option change flushes; the state is unchanged
+        assert abs(e.expval_z([0, n - 1]) - o.expval_z([0, n - 1])) < tol
+        if chi == 0:
+            assert np.abs(e.statevector() - o.statevector()).max() < tol
+        e.close()
+
+
+def test_norm_cache_is_invalidated_by_state_changes(O):
+    n = 8
+    e = tnqvm_b200.B200MPS(n, max_bond=4)
+    circ = Cc.brickwork(n, 6, seed=5)
+    e.run(circ)
+    e.expval_z_all()
+    n1 = e.norm()
+    o = O.OracleMPS(n, max_bond=4).run(circ)
+    assert abs(n1 - o.norm()) < TRUNC_TOL
+    more = Cc.brickwork(n, 2, seed=6)
+    e.run(more)
+    o.run(more)
+    assert abs(e.norm() - o.norm()) < TRUNC_TOL and abs(e.norm() - n1) > 1e-9
+    t = e.get_site(3)
+    e.set_site(3, 2.0 * t)
+    assert abs(e.norm() - 4.0 * o.norm()) < 4 * TRUNC_TOL
+    e.close()
+
+
 def test_config1_truncated_parity(O):
     # BASELINE config 1: 16-qubit GHZ + brickwork depth 10, max-bond-dim 64, per-qubit <Z>
     n = 16

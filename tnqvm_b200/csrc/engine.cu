@@ -316,7 +316,7 @@ struct mps_b200_handle {
     nlayers += 1;
     n2q += B;
 
-    struct Dim { int lo, cl, ch, cr, M, N, tall, Mg, Ng, Mj; size_t oT, oG, oY, oV, oTq, oCn2, oSig2, oSigma, oPerm, oSP, oSO, oKeep, oW; };
+    struct Dim { int lo, cl, ch, cr, M, N, tall, Mg, Ng, Mj; size_t oT, oG, oY, oV, oTq, oCn2, oWd, oSig2, oSigma, oPerm, oSP, oSO, oKeep, oW; };
     std::vector<Dim> D(B);
     ws.reset();
     // pass 1: sizes
@@ -360,6 +360,7 @@ struct mps_b200_handle {
     for (int b = 0; b < B; ++b) {
       Dim& d = D[b];
       d.oCn2 = ws.reserve(sizeof(double) * d.Ng);
+      d.oWd = ws.reserve(sizeof(double2) * 64 * (size_t)((d.Ng + 7) / 8));
       d.oSig2 = ws.reserve(sizeof(double) * d.Ng);
       d.oPerm = ws.reserve(sizeof(int) * d.Ng);
       d.oSP = ws.reserve(sizeof(double) * d.Ng);
@@ -413,7 +414,7 @@ struct mps_b200_handle {
       }
       j.nb = (d.Ng + 7) / 8;
       j.nbe = (j.nb == 1) ? 1 : ((j.nb + 1) & ~1);
-      j.cn2 = (double*)(wb + d.oCn2); j.thr = (double*)(wb + oThr) + b;
+      j.cn2 = (double*)(wb + d.oCn2); j.thr = (double*)(wb + oThr) + b; j.wd = (double2*)(wb + d.oWd);
       max_pairs = std::max(max_pairs, j.nb == 1 ? 1 : j.nbe / 2);
       max_steps = std::max(max_steps, j.nb == 1 ? 1 : j.nbe - 1);
       maxMg = std::max(maxMg, d.Mg);
@@ -916,6 +917,7 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     h->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("MPS_B200_JACOBI_TOL")) h->jacobi_tol = atof(e);
     if (const char* e = getenv("MPS_B200_NULL_TOL")) h->null_tol = atof(e);
+    if (const char* e = getenv("MPS_B200_3M")) jacobi_set_3m(atoi(e));
     if (seed) h->rng.seed(seed);
     else { std::random_device rd; h->rng.seed(rd()); }   // RandomEngine.hpp:39-42
     h->reset_state();
@@ -969,6 +971,7 @@ int mps_set_option(mps_handle_t h, const char* key, double value) {
   else if (k == "jacobi_groups") { h->flush(); h->jacobi_groups = std::max(1, (int)value); }
   else if (k == "jacobi_persistent") { h->flush(); h->jacobi_persistent = value != 0; }
   else if (k == "discard_margin") { h->flush(); h->discard_margin = value; }
+  else if (k == "jacobi_3m") { h->flush(); jacobi_set_3m(value != 0); }
   else if (k == "max_bond") h->max_bond = value > 0 ? (int)value : INT_MAX - 1;
   else if (k == "svd_cutoff") h->cutoff = value >= 0 ? value : DBL_MIN;
   else if (k == "gauge") h->gauge = (int)value;
@@ -1186,8 +1189,10 @@ int mps_resize_site(mps_handle_t h, int k, int dl, int dr, void** dptr) {
 }
 int mps_stats(mps_handle_t h, double* out, int cap) {
   API_BEGIN(h)
-  const double v[9] = {h->n2q, h->n1q, h->nlayers, h->nsweeps, h->nlaunch, h->ms_theta, h->ms_svd, h->ms_wb, h->ms_qr};
-  for (int i = 0; i < cap && i < 9; ++i) out[i] = v[i];
+  h->flush();
+  CK(cudaStreamSynchronize(h->stream));
+  const double v[10] = {h->n2q, h->n1q, h->nlayers, h->nsweeps, h->nlaunch, h->ms_theta, h->ms_svd, h->ms_wb, h->ms_qr, jacobi_dmma_flops()};
+  for (int i = 0; i < cap && i < 10; ++i) out[i] = v[i];
   API_END(h)
 }
 

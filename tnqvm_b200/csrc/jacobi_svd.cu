@@ -24,6 +24,7 @@ namespace {
 constexpr int JT = 128;     // threads per CTA (4 warps)
 constexpr int WLD = 17;     // padded leading dimension of the 16x16 shared matrices
 __device__ unsigned long long g_phase_cycles[8];   // developer timing (g_dbg_mode == 10): A, reduce+test, B, C, wait, tasks
+__device__ unsigned long long g_dmma_flops = 0;   // real flops executed on the DMMA pipe by the pair tasks (reporting only)
 __device__ int g_dbg_mode = 0;   // developer switches: 4 = rotate the pairs inside a block at every step (A/B run); 10 = per-phase clock64 timing
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -54,6 +55,7 @@ __device__ __forceinline__ bool pair_blocks(const JacobiProblem& P, int step, in
 // one pair task: Gram (phase A), rotations (phase B), apply (phase C) on the 16 columns of blocks (blkA, blkB).
 // All exits are uniform over the CTA.  Loads of G bypass L1 (ld.global.cg): inside the persistent sweep kernel the
 // columns were last written by a CTA on another SM.
+template <bool M3>
 __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int blkA, int blkB, bool within, double tol2, double dead2,
                                           const double* __restrict__ fro2, int* __restrict__ dirty) {
   const int M = P.M, N = P.N, ldg = P.ldg;
@@ -91,6 +93,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     if (tid == 0) s_need = 0;
     __syncthreads();
   }
+  if (!within && blkB < 0) return;   // a lone block has no cross pairs
   const bool timing = (g_dbg_mode == 10) && tid == 0;
   long long tA = 0, tB = 0, tC = 0, tD = 0;
   if (timing) tA = clock64();
@@ -104,6 +107,28 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     double w00[2] = {0, 0}, m00[2] = {0, 0}, w11[2] = {0, 0}, m11[2] = {0, 0}, w01[2] = {0, 0}, p01[2] = {0, 0}, q01[2] = {0, 0};
     const int nch = (M + 3) >> 2;
     constexpr int UN = 4;
+    if (!within) {
+      // only the cross block W_AB = X_A^H X_B is computed (4 DMMA per 4 rows instead of 10): the Gram blocks W_AA, W_BB
+      // of the two column blocks travel with them (P.wd), kept up to date by the two-sided rotations of every task and
+      // recomputed from the columns at the first step of each tournament
+      for (int base = warp * UN; base < nch; base += 4 * UN) {
+        double2 x0[UN], x1[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int row = 4 * (base + u) + rsub;
+          const bool ok = row < M;
+          x0[u] = (ok && p0) ? __ldcg(p0 + row) : make_double2(0.0, 0.0);
+          x1[u] = (ok && p1) ? __ldcg(p1 + row) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          dmma884(w01[0], w01[1], x0[u].x, x1[u].x);
+          dmma884(p01[0], p01[1], x0[u].x, x1[u].y);
+          dmma884(q01[0], q01[1], x0[u].y, x1[u].x);
+          dmma884(w01[0], w01[1], x0[u].y, x1[u].y);
+        }
+      }
+    } else
     for (int base = warp * UN; base < nch; base += 4 * UN) {
       double2 x0[UN], x1[UN];
 #pragma unroll
@@ -139,16 +164,19 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   }
   __syncthreads();
   if (timing) tB = clock64();
-  for (int i = tid; i < 7 * 64; i += JT) {
+  for (int i = tid + (within ? 0 : 4 * 64); i < 7 * 64; i += JT) {
     const int t = i >> 6, e = i & 63;
     s_red[0][t][e] = s_red[0][t][e] + s_red[1][t][e] + s_red[2][t][e] + s_red[3][t][e];
   }
   __syncthreads();
+  const double2* wdA = P.wd + (size_t)blkA * 64;
+  const double2* wdB = P.wd + (size_t)(blkB >= 0 ? blkB : blkA) * 64;
   for (int i = tid; i < 256; i += JT) {
     const int p = i >> 4, q = i & 15;
     const int bp = p >> 3, bq = q >> 3, r = p & 7, c = q & 7;
     double re, im;
-    if (bp == 0 && bq == 0) { re = s_red[0][0][r * 8 + c]; im = s_red[0][1][r * 8 + c] - s_red[0][1][c * 8 + r]; }
+    if (bp == bq && !within) { const double2 v = __ldcg((bp ? wdB : wdA) + r * 8 + c); re = v.x; im = v.y; }
+    else if (bp == 0 && bq == 0) { re = s_red[0][0][r * 8 + c]; im = s_red[0][1][r * 8 + c] - s_red[0][1][c * 8 + r]; }
     else if (bp == 1 && bq == 1) { re = s_red[0][2][r * 8 + c]; im = s_red[0][3][r * 8 + c] - s_red[0][3][c * 8 + r]; }
     else if (bp == 0) { re = s_red[0][4][r * 8 + c]; im = s_red[0][5][r * 8 + c] - s_red[0][6][r * 8 + c]; }
     else { re = s_red[0][4][c * 8 + r]; im = -(s_red[0][5][c * 8 + r] - s_red[0][6][c * 8 + r]); }
@@ -173,8 +201,14 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   if (timing) { tC = clock64(); atomicAdd(&g_phase_cycles[0], (unsigned long long)(tB - tA)); atomicAdd(&g_phase_cycles[1], (unsigned long long)(tC - tB)); atomicAdd(&g_phase_cycles[5], 1ull); }
   if (!s_need) {
     if (tid < 16 && s_cols[tid] >= 0) P.cn2[s_cols[tid]] = sW[tid * WLD + tid].x;
+    if (within) {   // the tournament's first step refreshes the travelling Gram blocks from the columns
+      const int bb = tid >> 6, r = (tid >> 3) & 7, c = tid & 7;
+      if (bb == 0 || blkB >= 0) P.wd[(size_t)(bb ? blkB : blkA) * 64 + r * 8 + c] = sW[(8 * bb + r) * WLD + 8 * bb + c];
+    }
+    if (tid == 0) atomicAdd(&g_dmma_flops, (unsigned long long)((M + 3) >> 2) * (within ? 5120ull : 2048ull));   // Gram: 10 (4) DMMA per 4 rows
     return;
   }
+  if (tid == 0) atomicAdd(&g_dmma_flops, (unsigned long long)((M + 3) >> 2) * (within ? 5120ull : 2048ull) + (unsigned long long)((M + 7) >> 3) * (M3 ? 12288ull : 16384ull));
   if (tid == 0) dirty[mat] = 1;
 
   // ------------------------------------------------------------------ phase B: Jacobi rotations on W (all four warps)
@@ -248,6 +282,10 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     }
   }
   if (tid < 16 && s_cols[tid] >= 0) P.cn2[s_cols[tid]] = sW[tid * WLD + tid].x;   // the last round ended with a barrier
+  {
+    const int bb = tid >> 6, r = (tid >> 3) & 7, c = tid & 7;
+    if (bb == 0 || blkB >= 0) P.wd[(size_t)(bb ? blkB : blkA) * 64 + r * 8 + c] = sW[(8 * bb + r) * WLD + 8 * bb + c];
+  }
   __syncthreads();
   if (timing) { tD = clock64(); atomicAdd(&g_phase_cycles[2], (unsigned long long)(tD - tC)); }
 
@@ -258,6 +296,11 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     for (int k4 = 0; k4 < 4; ++k4)
 #pragma unroll
       for (int jn = 0; jn < 2; ++jn) qf[k4][jn] = sQ[(4 * k4 + (lane & 3)) * WLD + 8 * jn + (lane >> 2)];
+    double qs[4][2];
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4)
+#pragma unroll
+      for (int jn = 0; jn < 2; ++jn) qs[k4][jn] = qf[k4][jn].x + qf[k4][jn].y;
     const double2* src[4];
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4) {
@@ -285,6 +328,29 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         double re[2][2] = {{0, 0}, {0, 0}}, im[2][2] = {{0, 0}, {0, 0}};
+        if (M3) {
+          // 3M complex product: T1 = Xr Qr, T2 = Xi Qi, T3 = (Xr + Xi)(Qr + Qi);  Re = T1 - T2, Im = T3 - T1 - T2
+          // (24 instead of 32 DMMA per 8 rows; the error stays of order eps |X| |Q| per term)
+          double t2[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const double ar = xa[u][k4].x, ai = xa[u][k4].y, as = ar + ai;
+#pragma unroll
+            for (int jn = 0; jn < 2; ++jn) {
+              dmma884(re[jn][0], re[jn][1], ar, qf[k4][jn].x);
+              dmma884(t2[jn][0], t2[jn][1], ai, qf[k4][jn].y);
+              dmma884(im[jn][0], im[jn][1], as, qs[k4][jn]);
+            }
+          }
+#pragma unroll
+          for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const double t1 = re[jn][e];
+              re[jn][e] = t1 - t2[jn][e];
+              im[jn][e] = im[jn][e] - t1 - t2[jn][e];
+            }
+        } else {
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const double ar = xa[u][k4].x, ai = xa[u][k4].y, nai = -ai;
@@ -295,6 +361,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
             dmma884(re[jn][0], re[jn][1], nai, qf[k4][jn].y);
             dmma884(im[jn][0], im[jn][1], ai, qf[k4][jn].x);
           }
+        }
         }
         const int row = 8 * (base + u) + (lane >> 2);
         if (row < M) {
@@ -311,6 +378,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
 }
 
 // One step of the tournament for the whole batch (grid = pairs x matrices); kept for A/B runs (option "jacobi_persistent" 0).
+template <bool M3>
 __global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem* __restrict__ probs, int step, double tol2, double dead2,
                                                             const double* __restrict__ fro2, int* __restrict__ dirty,
                                                             const int* __restrict__ done) {
@@ -322,7 +390,7 @@ __global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem*
   int blkA, blkB;
   bool within;
   if (!pair_blocks(P, step, blockIdx.x, blkA, blkB, within)) return;
-  pair_task(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
+  pair_task<M3>(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
 }
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -338,6 +406,7 @@ __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.rel
 // Tasks are dequeued in dependency order and a waiting CTA only waits on tasks dequeued before its own, which are
 // finished or running on resident CTAs, so the scheme cannot deadlock.  Compared with one launch per step this removes
 // ~60 launch boundaries per sweep and lets the Gram / rotate / apply phases of different pairs overlap on an SM.
+template <bool M3>
 __global__ void __launch_bounds__(JT, 4) jacobi_sweep_kernel(const JacobiProblem* __restrict__ probs, int batch, int max_pairs, int nsteps,
                                                              int base, double tol2, double dead2, const double* __restrict__ fro2,
                                                              int* __restrict__ dirty, const int* __restrict__ done,
@@ -381,7 +450,7 @@ __global__ void __launch_bounds__(JT, 4) jacobi_sweep_kernel(const JacobiProblem
     }
     __syncthreads();
     if (threadIdx.x == 0 && g_dbg_mode == 10) atomicAdd(&g_phase_cycles[4], (unsigned long long)(clock64() - tw));
-    pair_task(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
+    pair_task<M3>(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -528,11 +597,14 @@ __global__ void gather_kernel(const GatherProblem* __restrict__ probs) {
 
 }  // namespace
 
+static bool g_use_3m = false;   // measured on B200: the column update is L2-bandwidth-bound, 3M does not pay (profiles/)
+void jacobi_set_3m(int on) { g_use_3m = on != 0; }
 void launch_jacobi_step(const JacobiProblem* d_probs, int batch, int max_pairs, int step, double tol2, double dead2,
                         const double* d_fro2, int* d_dirty, const int* d_done, cudaStream_t s) {
   if (batch <= 0) return;
   dim3 grid(max_pairs, batch);
-  jacobi_step_kernel<<<grid, JT, 0, s>>>(d_probs, step, tol2, dead2, d_fro2, d_dirty, d_done);
+  if (g_use_3m) jacobi_step_kernel<true><<<grid, JT, 0, s>>>(d_probs, step, tol2, dead2, d_fro2, d_dirty, d_done);
+  else jacobi_step_kernel<false><<<grid, JT, 0, s>>>(d_probs, step, tol2, dead2, d_fro2, d_dirty, d_done);
 }
 void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
                          const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
@@ -540,12 +612,21 @@ void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs,
   if (batch <= 0) return;
   const long total = (long)nsteps * batch * max_pairs;
   const int grid = (int)std::min<long>(total, grid_ctas);
-  jacobi_sweep_kernel<<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done, d_progress,
-                                          progress_stride, d_counter, d_fault, stagger_ns);
+  if (g_use_3m)
+    jacobi_sweep_kernel<true><<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done, d_progress,
+                                                  progress_stride, d_counter, d_fault, stagger_ns);
+  else
+    jacobi_sweep_kernel<false><<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
+                                                   d_progress, progress_stride, d_counter, d_fault, stagger_ns);
 }
 void launch_jacobi_thr(const JacobiProblem* d_probs, int batch, int keep, double margin, const int* d_done, cudaStream_t s) {
   if (batch <= 0 || keep <= 0 || margin <= 0.0) return;
   jacobi_thr_kernel<<<batch, 256, 48 * 1024, s>>>(d_probs, keep, margin, d_done);
+}
+double jacobi_dmma_flops() {
+  unsigned long long v = 0;
+  cudaMemcpyFromSymbol(&v, g_dmma_flops, sizeof(v));
+  return (double)v;
 }
 void jacobi_set_debug_mode(int mode) { cudaMemcpyToSymbol(g_dbg_mode, &mode, sizeof(int)); }
 void jacobi_print_phase_timing() {

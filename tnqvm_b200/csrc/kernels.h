@@ -60,6 +60,7 @@ struct JacobiProblem {
   // *thr are both certain to be truncated and need not be orthogonalised against each other.
   double* cn2;
   double* thr;
+  double2* wd;   // nb travelling 8x8 Gram blocks (row-major, 64 complex each): W_BB of every column block
 };
 // per sweep: *thr = margin * (keep-th largest cn2) for every matrix with N > keep that is still rotating
 void launch_jacobi_thr(const JacobiProblem* d_probs, int batch, int keep, double margin, const int* d_done, cudaStream_t s);
@@ -72,6 +73,8 @@ void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs,
                          int* d_fault, int grid_ctas, int stagger_ns, cudaStream_t s);   // *d_fault += 1 if a dependency wait timed out
 void jacobi_set_debug_mode(int mode);   // timing experiments only
 void jacobi_print_phase_timing();
+void jacobi_set_3m(int on);   // 3M complex product in the column update (default off); process-wide
+double jacobi_dmma_flops();   // process-wide count of real flops the Jacobi pair tasks issued on the DMMA pipe
 void launch_fro2(const JacobiProblem* d_probs, int batch, double* d_fro2, cudaStream_t s);   // d_fro2 pre-zeroed
 // after a sweep: done[m] |= !dirty[m]; dirty[m] = 0; *remaining = #not done
 void launch_jacobi_check(int batch, int* d_dirty, int* d_done, int* d_remaining, cudaStream_t s);
