@@ -55,64 +55,137 @@ __global__ void __launch_bounds__(PT, 1) qr_panel_kernel(const QrProblem* __rest
   int ld;
   if (in_smem) {
     Pn = sp; ld = mk;
-    for (int c = warp; c < pw; c += PB)
-      for (int i = lane; i < mk; i += 32) sp[i + (size_t)mk * c] = gp[i + (size_t)P.ldy * c];
+    // the panel is pw columns of mk contiguous elements: every thread keeps four independent 16-byte loads in flight
+    const int total = mk * pw;
+    for (int e0 = tid * 4; e0 < total; e0 += PT * 4) {
+      double2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u;
+        if (e < total) { const int c = e / mk, i = e - c * mk; v[u] = gp[i + (size_t)P.ldy * c]; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e0 + u < total) sp[e0 + u] = v[u];
+    }
   } else {
     Pn = gp; ld = P.ldy;
   }
   __syncthreads();
 
-  for (int j = 0; j < pw; ++j) {
-    if (warp == j) {
-      double2* x = Pn + (size_t)ld * j;
-      double s = 0.0;
-      for (int i = j + 1 + lane; i < mk; i += 32) { const double2 v = x[i]; s += v.x * v.x + v.y * v.y; }
-      s = warp_sum(s);
-      const double2 alpha = x[j];
-      double2 tau = make_double2(0.0, 0.0);
-      if (s > 0.0) {
-        // zlarfg: beta = -sign(re alpha) * ||(alpha, x)||, tau = (beta - alpha)/beta, v = x / (alpha - beta)
-        const double an = sqrt(alpha.x * alpha.x + alpha.y * alpha.y + s);
-        const double beta = alpha.x >= 0.0 ? -an : an;
-        tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
-        const double dx = alpha.x - beta, dy = alpha.y;
-        const double dn = 1.0 / (dx * dx + dy * dy);
-        const double2 inv = make_double2(dx * dn, -dy * dn);
-        for (int i = j + 1 + lane; i < mk; i += 32) x[i] = cmul(x[i], inv);
-        if (lane == 0) x[j] = make_double2(beta, 0.0);
-      }
-      if (lane == 0) s_tau[j] = tau;
+  // squared norm of the part of column 0 below the diagonal (each later column gets its own while it is updated)
+  // The reflector vectors stay UNSCALED in the panel while it is factored (v_j = x_j * inv_j below the diagonal, 1 on it):
+  // the warps that apply reflector j read column j while warp j only touches its diagonal, so there is no race and no
+  // extra barrier; the scale is applied where V is written out.
+  __shared__ double s_nrm[PB];
+  __shared__ double2 s_inv[PB];
+  if (warp == 0) {
+    const double2* x = Pn;
+    double s0 = 0.0, s1 = 0.0;
+    int i = 1 + lane;
+    for (; i + 32 < mk; i += 64) {
+      const double2 a = x[i], b = x[i + 32];
+      s0 += a.x * a.x + a.y * a.y; s1 += b.x * b.x + b.y * b.y;
     }
-    __syncthreads();
-    if (warp > j && warp < pw) {
-      const double2 tau = s_tau[j];
-      if (tau.x != 0.0 || tau.y != 0.0) {
-        const double2* v = Pn + (size_t)ld * j;
-        double2* a = Pn + (size_t)ld * warp;
-        double wr = 0.0, wi = 0.0;
-        for (int i = j + 1 + lane; i < mk; i += 32) { const double2 t = cmulc(v[i], a[i]); wr += t.x; wi += t.y; }
-        wr = warp_sum(wr); wi = warp_sum(wi);
-        const double2 aj = a[j];
-        const double2 w = make_double2(wr + aj.x, wi + aj.y);           // v^H a, v(j) = 1
-        const double2 f = cmul(make_double2(tau.x, -tau.y), w);         // conj(tau) * w :  H^H a = a - conj(tau) v (v^H a)
-        for (int i = j + 1 + lane; i < mk; i += 32) { const double2 t = cmul(f, v[i]); a[i].x -= t.x; a[i].y -= t.y; }
-        if (lane == 0) a[j] = make_double2(aj.x - f.x, aj.y - f.y);
+    if (i < mk) { const double2 a = x[i]; s0 += a.x * a.x + a.y * a.y; }
+    s0 = warp_sum(s0 + s1);
+    if (lane == 0) s_nrm[0] = s0;
+  }
+  __syncthreads();
+
+  for (int j = 0; j < pw; ++j) {
+    // every warp derives reflector j's scalars redundantly from column j's diagonal entry and tail norm (no extra barrier)
+    const double2 alpha = Pn[j + (size_t)ld * j];
+    const double s = s_nrm[j];
+    double2 tau = make_double2(0.0, 0.0), inv = make_double2(0.0, 0.0);
+    double beta = 0.0;
+    const bool live = s > 0.0;
+    if (live) {
+      // zlarfg: beta = -sign(re alpha) * ||(alpha, x)||, tau = (beta - alpha)/beta, v = x / (alpha - beta)
+      const double an = sqrt(alpha.x * alpha.x + alpha.y * alpha.y + s);
+      beta = alpha.x >= 0.0 ? -an : an;
+      tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
+      const double dx = alpha.x - beta, dy = alpha.y;
+      const double dn = 1.0 / (dx * dx + dy * dy);
+      inv = make_double2(dx * dn, -dy * dn);
+    }
+    if (tid == 0) { s_tau[j] = tau; s_inv[j] = inv; }
+    __syncthreads();   // everybody has read alpha before warp j overwrites it
+    if (warp == j) {
+      if (live && lane == 0) Pn[j + (size_t)ld * j] = make_double2(beta, 0.0);
+    } else if (warp > j && warp < pw && live) {
+      // a <- H^H a = a - conj(tau) v (v^H a) with v = x * inv below the diagonal, v(j) = 1
+      const double2* x = Pn + (size_t)ld * j;
+      double2* a = Pn + (size_t)ld * warp;
+      double wr0 = 0.0, wi0 = 0.0, wr1 = 0.0, wi1 = 0.0;
+      int i = j + 1 + lane;
+      for (; i + 32 < mk; i += 64) {
+        const double2 t0 = cmulc(x[i], a[i]), t1 = cmulc(x[i + 32], a[i + 32]);
+        wr0 += t0.x; wi0 += t0.y; wr1 += t1.x; wi1 += t1.y;
       }
+      if (i < mk) { const double2 t0 = cmulc(x[i], a[i]); wr0 += t0.x; wi0 += t0.y; }
+      const double xr = warp_sum(wr0 + wr1), xi = warp_sum(wi0 + wi1);
+      // v^H a = conj(inv) * (x^H a) + a_j
+      const double2 aj = a[j];
+      const double2 xa = cmul(make_double2(inv.x, -inv.y), make_double2(xr, xi));
+      const double2 w = make_double2(xa.x + aj.x, xa.y + aj.y);
+      const double2 f = cmul(make_double2(tau.x, -tau.y), w);         // conj(tau) * (v^H a)
+      const double2 fi = cmul(f, inv);                                 // a_i -= f * v_i = (f * inv) * x_i
+      double n0 = 0.0, n1 = 0.0;
+      const bool next = (warp == j + 1);                               // this column is the next reflector: take its tail norm now
+      i = j + 1 + lane;
+      for (; i + 32 < mk; i += 64) {
+        const double2 u0 = cmul(fi, x[i]), u1 = cmul(fi, x[i + 32]);
+        double2 b0 = a[i], b1 = a[i + 32];
+        b0.x -= u0.x; b0.y -= u0.y; b1.x -= u1.x; b1.y -= u1.y;
+        a[i] = b0; a[i + 32] = b1;
+        if (next) { if (i > j + 1) n0 += b0.x * b0.x + b0.y * b0.y; n1 += b1.x * b1.x + b1.y * b1.y; }
+      }
+      if (i < mk) {
+        const double2 u0 = cmul(fi, x[i]);
+        double2 b0 = a[i];
+        b0.x -= u0.x; b0.y -= u0.y;
+        a[i] = b0;
+        if (next && i > j + 1) n0 += b0.x * b0.x + b0.y * b0.y;
+      }
+      if (lane == 0) a[j] = make_double2(aj.x - f.x, aj.y - f.y);
+      if (next) { n0 = warp_sum(n0 + n1); if (lane == 0) s_nrm[j + 1] = n0; }
+    } else if (warp == j + 1 && warp < pw && !live) {
+      // H_j = I: column j+1 is unchanged, its tail norm is still needed
+      const double2* a = Pn + (size_t)ld * warp;
+      double n0 = 0.0;
+      for (int i = j + 2 + lane; i < mk; i += 32) { const double2 b0 = a[i]; n0 += b0.x * b0.x + b0.y * b0.y; }
+      n0 = warp_sum(n0);
+      if (lane == 0) s_nrm[j + 1] = n0;
     }
     __syncthreads();
   }
 
-  // S = V^H V (strict upper part), V unit lower trapezoidal
-  for (int pr = warp; pr < PB * PB; pr += PB) {
-    const int a = pr / PB, b = pr % PB;
-    if (a < b && b < pw) {
-      const double2* va = Pn + (size_t)ld * a;
-      const double2* vb = Pn + (size_t)ld * b;
-      double sr = 0.0, si = 0.0;
-      for (int i = b + 1 + lane; i < mk; i += 32) { const double2 t = cmulc(va[i], vb[i]); sr += t.x; si += t.y; }
-      sr = warp_sum(sr); si = warp_sum(si);
-      if (lane == 0) { const double2 h = va[b]; sS[a][b] = make_double2(sr + h.x, si - h.y); }   // + conj(V[b][a]) * 1
+  // S = V^H V (strict upper part), V unit lower trapezoidal: warp b forms S(0:b, b) in one pass over its column
+  if (warp < pw && warp > 0) {
+    const int b = warp;
+    const double2* vb = Pn + (size_t)ld * b;
+    double sr[PB - 1], si[PB - 1];
+#pragma unroll
+    for (int a = 0; a < PB - 1; ++a) { sr[a] = 0.0; si[a] = 0.0; }
+    for (int i = b + 1 + lane; i < mk; i += 32) {
+      const double2 y = vb[i];
+#pragma unroll
+      for (int a = 0; a < PB - 1; ++a)
+        if (a < b) { const double2 t = cmulc(Pn[i + (size_t)ld * a], y); sr[a] += t.x; si[a] += t.y; }
     }
+#pragma unroll
+    for (int a = 0; a < PB - 1; ++a)
+      if (a < b) {
+        const double r = warp_sum(sr[a]), im = warp_sum(si[a]);
+        if (lane == 0) {
+          // v_a^H v_b = conj(inv_a) inv_b (x_a^H x_b)(rows > b) + conj(inv_a x_a[b]) * 1
+          const double2 ia = s_inv[a], ib = s_inv[b];
+          const double2 t = cmul(cmulc(ia, ib), make_double2(r, im));
+          const double2 h = cmul(ia, Pn[b + (size_t)ld * a]);
+          sS[a][b] = make_double2(t.x + h.x, t.y - h.y);
+        }
+      }
   }
   for (int i = tid; i < PB * PB; i += PT) sT[i / PB][i % PB] = make_double2(0.0, 0.0);
   __syncthreads();
@@ -132,21 +205,21 @@ __global__ void __launch_bounds__(PT, 1) qr_panel_kernel(const QrProblem* __rest
   }
   __syncthreads();
   for (int i = tid; i < PB * PB; i += PT) P.T[i] = sT[i % PB][i / PB];   // column-major PB x PB
-  // clean reflector block for the update kernel: V (mk x PB, ld = P.M), unit diagonal, zeros above and beyond pw
-  for (int c = warp; c < PB; c += PB) {
-    double2* vout = P.V + (size_t)P.M * c;
-    for (int i = lane; i < mk; i += 32) {
+  // clean reflector block for the update kernel: V (mk x PB, ld = P.M), unit diagonal, zeros above and beyond pw;
+  // and the panel itself back to global memory
+  {
+    const int total = mk * PB;
+    for (int e = tid; e < total; e += PT) {
+      const int c = e / mk, i = e - c * mk;
       double2 v = make_double2(0.0, 0.0);
       if (c < pw) {
+        const double2 x = Pn[i + (size_t)ld * c];
+        if (in_smem) gp[i + (size_t)P.ldy * c] = x;
         if (i == c) v = make_double2(1.0, 0.0);
-        else if (i > c) v = Pn[i + (size_t)ld * c];
+        else if (i > c) v = cmul(x, s_inv[c]);
       }
-      vout[i] = v;
+      P.V[i + (size_t)P.M * c] = v;
     }
-  }
-  if (in_smem) {
-    for (int c = warp; c < pw; c += PB)
-      for (int i = lane; i < mk; i += 32) gp[i + (size_t)P.ldy * c] = sp[i + (size_t)mk * c];
   }
 }
 
