@@ -237,7 +237,7 @@ def test_multi_register_batch_equals_separate_runs():
     eb.close()
 
 
-@pytest.mark.parametrize("chi", [64, 256])
+@pytest.mark.parametrize("chi", [64, 256, 512])
 def test_full_size_properties(chi):
     """BASELINE full sizes through size-independent properties: a saturated-bond 2q gate followed by its inverse
     restores the state (round trip), the untruncated split reproduces theta, norm is conserved."""
@@ -263,4 +263,40 @@ def test_full_size_properties(chi):
     assert np.abs(e.expval_z_all() - z0).max() < 1e-10 * abs(nrm0)
     s = e.singular_values(2)
     assert np.all(np.diff(s) <= 1e-18) and s.min() >= 0   # sorted descending
+    e.close()
+
+
+@pytest.mark.parametrize("chi,gauge", [(256, 0), (256, 1), (96, 2), (320, 0)])
+def test_full_size_truncated_gate_against_lapack(chi, gauge):
+    """One saturated-bond gate at BASELINE size with truncation 2 chi -> chi active, checked against LAPACK (numpy) on the same
+    theta: retained singular values, discarded weight, and the product of the two new sites = the best rank-chi approximation
+    (unique when sigma_chi > sigma_chi+1, which holds for these Gaussian sites).  chi = 320 exercises the QR panel's
+    global-memory path (640 rows > the shared-memory panel), chi = 96 a bond that is not a multiple of the 8-column block."""
+    rng = np.random.default_rng(chi + gauge)
+    n = 4
+    dims = [1, chi, chi, chi, 1]
+    e = tnqvm_b200.B200MPS(n, max_bond=chi, gauge=gauge)
+    S = []
+    for k in range(n):
+        t = (rng.standard_normal((dims[k], 2, dims[k + 1])) + 1j * rng.standard_normal((dims[k], 2, dims[k + 1]))) / math.sqrt(2 * dims[k] * dims[k + 1])
+        S.append(t); e.set_site(k, t)
+    m = tnqvm_b200.gates.gate_matrix("fSim", (0.4, 1.1))
+    e.apply_2q(1, 2, m)
+    A, B = e.get_site(1), e.get_site(2)
+    assert A.shape == (chi, 2, chi) and B.shape == (chi, 2, chi)
+    th = np.einsum('pqij,aijc->apqc', m.reshape(2, 2, 2, 2), np.einsum('apk,kqc->apqc', S[1], S[2])).reshape(2 * chi, 2 * chi)
+    U, sv, Vh = np.linalg.svd(th)
+    best = (U[:, :chi] * sv[:chi]) @ Vh[:chi]
+    got = np.einsum('apk,kqc->apqc', A, B).reshape(2 * chi, 2 * chi)
+    assert np.abs(got - best).max() < 1e-11 * sv[0]
+    s = e.singular_values(1)
+    assert len(s) == chi and np.abs(s - sv[:chi]).max() < 1e-12 * sv[0]
+    w = e.discarded_weight()
+    assert abs(w - (sv[chi:] ** 2).sum() / (sv ** 2).sum()) < 1e-12
+    if gauge == 1:     # orthogonality centre moved right: the left site is an isometry
+        Am = A.reshape(2 * chi, chi)
+        assert np.abs(Am.conj().T @ Am - np.eye(chi)).max() < 1e-12
+    if gauge == 2:
+        Bm = B.reshape(chi, 2 * chi)
+        assert np.abs(Bm @ Bm.conj().T - np.eye(chi)).max() < 1e-12
     e.close()

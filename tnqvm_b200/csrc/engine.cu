@@ -316,7 +316,7 @@ struct mps_b200_handle {
     nlayers += 1;
     n2q += B;
 
-    struct Dim { int lo, cl, ch, cr, M, N, tall, Mg, Ng, Mj; size_t oT, oG, oY, oV, oTq, oCn2, oWd, oSig2, oSigma, oPerm, oSP, oSO, oKeep, oW; };
+    struct Dim { int lo, cl, ch, cr, M, N, tall, Mg, Ng, Mj; size_t oT, oG, oY, oV, oTq, oCn2, oWd, oVer, oSig2, oSigma, oPerm, oSP, oSO, oKeep, oW; };
     std::vector<Dim> D(B);
     ws.reset();
     // pass 1: sizes
@@ -361,6 +361,10 @@ struct mps_b200_handle {
       Dim& d = D[b];
       d.oCn2 = ws.reserve(sizeof(double) * d.Ng);
       d.oWd = ws.reserve(sizeof(double2) * 64 * (size_t)((d.Ng + 7) / 8));
+      {
+        const size_t nbe_ = (size_t)((((d.Ng + 7) / 8) + 1) & ~1);
+        d.oVer = ws.reserve(sizeof(int) * nbe_ + 8 + sizeof(int2) * nbe_ * nbe_);   // versions, then the clean-pair memo
+      }
       d.oSig2 = ws.reserve(sizeof(double) * d.Ng);
       d.oPerm = ws.reserve(sizeof(int) * d.Ng);
       d.oSP = ws.reserve(sizeof(double) * d.Ng);
@@ -415,6 +419,12 @@ struct mps_b200_handle {
       j.nb = (d.Ng + 7) / 8;
       j.nbe = (j.nb == 1) ? 1 : ((j.nb + 1) & ~1);
       j.cn2 = (double*)(wb + d.oCn2); j.thr = (double*)(wb + oThr) + b; j.wd = (double2*)(wb + d.oWd);
+      {
+        const size_t nbe_ = (size_t)((j.nb + 1) & ~1);
+        j.ver = (int*)(wb + d.oVer);
+        j.rec = (int2*)(wb + d.oVer + ((sizeof(int) * nbe_ + 7) & ~size_t(7)));
+        CK(cudaMemsetAsync(wb + d.oVer, 0, sizeof(int) * nbe_ + 8 + sizeof(int2) * nbe_ * nbe_, stream));
+      }
       max_pairs = std::max(max_pairs, j.nb == 1 ? 1 : j.nbe / 2);
       max_steps = std::max(max_steps, j.nb == 1 ? 1 : j.nbe - 1);
       maxMg = std::max(maxMg, d.Mg);

@@ -94,6 +94,18 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     __syncthreads();
   }
   if (!within && blkB < 0) return;   // a lone block has no cross pairs
+  // Clean-pair memo: ver[b] counts the rotations block b has been through; rec[A][B] remembers the two versions at which the
+  // cross pairs of (A, B) were last found orthogonal.  If neither block has changed since, the task is over before it loads
+  // a single column -- this is what makes the last sweeps of a nearly converged matrix (and the final confirming sweep) cheap.
+  int verA = 0, verB = 0;
+  int2* recp = nullptr;
+  if (!within) {
+    verA = __ldcg(P.ver + blkA); verB = __ldcg(P.ver + blkB);
+    recp = P.rec + (size_t)min(blkA, blkB) * P.nbe + max(blkA, blkB);
+    const int2 rec = __ldcg(recp);
+    const int va = blkA < blkB ? verA : verB, vb = blkA < blkB ? verB : verA;
+    if (rec.x == va + 1 && rec.y == vb + 1) return;   // uniform: every thread read the same words
+  }
   const bool timing = (g_dbg_mode == 10) && tid == 0;
   long long tA = 0, tB = 0, tC = 0, tD = 0;
   if (timing) tA = clock64();
@@ -201,6 +213,10 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   if (timing) { tC = clock64(); atomicAdd(&g_phase_cycles[0], (unsigned long long)(tB - tA)); atomicAdd(&g_phase_cycles[1], (unsigned long long)(tC - tB)); atomicAdd(&g_phase_cycles[5], 1ull); }
   if (!s_need) {
     if (tid < 16 && s_cols[tid] >= 0) P.cn2[s_cols[tid]] = sW[tid * WLD + tid].x;
+    if (!within && tid == 0) {
+      const int va = blkA < blkB ? verA : verB, vb = blkA < blkB ? verB : verA;
+      *recp = make_int2(va + 1, vb + 1);
+    }
     if (within) {   // the tournament's first step refreshes the travelling Gram blocks from the columns
       const int bb = tid >> 6, r = (tid >> 3) & 7, c = tid & 7;
       if (bb == 0 || blkB >= 0) P.wd[(size_t)(bb ? blkB : blkA) * 64 + r * 8 + c] = sW[(8 * bb + r) * WLD + 8 * bb + c];
@@ -282,6 +298,11 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     }
   }
   if (tid < 16 && s_cols[tid] >= 0) P.cn2[s_cols[tid]] = sW[tid * WLD + tid].x;   // the last round ended with a barrier
+  if (tid == 0) {   // this task is the only owner of both blocks during this step
+    if (within) { verA = __ldcg(P.ver + blkA); if (blkB >= 0) verB = __ldcg(P.ver + blkB); }
+    P.ver[blkA] = verA + 1;
+    if (blkB >= 0) P.ver[blkB] = verB + 1;
+  }
   {
     const int bb = tid >> 6, r = (tid >> 3) & 7, c = tid & 7;
     if (bb == 0 || blkB >= 0) P.wd[(size_t)(bb ? blkB : blkA) * 64 + r * 8 + c] = sW[(8 * bb + r) * WLD + 8 * bb + c];

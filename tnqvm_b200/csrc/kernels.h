@@ -61,6 +61,8 @@ struct JacobiProblem {
   double* cn2;
   double* thr;
   double2* wd;   // nb travelling 8x8 Gram blocks (row-major, 64 complex each): W_BB of every column block
+  int* ver;      // nb block versions (rotations seen), zeroed per SVD
+  int2* rec;     // nbe x nbe clean-pair memo: versions (+1) of (A < B) at which their cross pairs were last found clean; zeroed per SVD
 };
 // per sweep: *thr = margin * (keep-th largest cn2) for every matrix with N > keep that is still rotating
 void launch_jacobi_thr(const JacobiProblem* d_probs, int batch, int keep, double margin, const int* d_done, cudaStream_t s);
