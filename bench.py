@@ -390,7 +390,7 @@ def run_b200(args):
         tf = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tf):
             try:
-                traffic = json.load(open(tf)).get("svd_bytes_per_step")
+                traffic = json.load(open(tf)).get("jacobi_sweep_dram_bytes_per_launch")   # ncu capture, see the file
             except Exception:
                 traffic = None
         svd_tf = sv_fl / (ms_svd * 1e-3) / 1e12 if ms_svd > 0 else None

@@ -300,3 +300,22 @@ def test_full_size_truncated_gate_against_lapack(chi, gauge):
         Bm = B.reshape(chi, 2 * chi)
         assert np.abs(Bm @ Bm.conj().T - np.eye(chi)).max() < 1e-12
     e.close()
+
+
+def test_site_sharded_over_nccl_matches_single_gpu():
+    """Config 3/5 style: MPS sites sharded over the GPUs of the box, boundary bond tensors over NCCL P2P; needs >= 2 GPUs
+    (the CPU gloo tests in test_sharded_host.py cover the same host logic with world sizes 2 and 3)."""
+    import subprocess
+    import sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(ngpu, 4)), "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(root, "scripts", "sharded_check.py"), "--qubits", "20", "--depth", "10", "--chi", "32"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["max_abs_dz"] < TRUNC_TOL and out["abs_dnorm"] < TRUNC_TOL and out["boundary_exchanges"] > 0
