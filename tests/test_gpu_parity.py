@@ -319,3 +319,41 @@ def test_site_sharded_over_nccl_matches_single_gpu():
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert out["max_abs_dz"] < TRUNC_TOL and out["abs_dnorm"] < TRUNC_TOL and out["boundary_exchanges"] > 0
+
+
+def test_config3_qaoa_ring_zz_energy(O):
+    """BASELINE config 3 scaled to oracle size: ring MaxCut QAOA (the wrap edge routed by the nearest-neighbour pass),
+    <Z_i Z_j> on every ring edge and the cut energy sum (1 - <ZZ>)/2; exact, and with truncation active.  QAOA states carry
+    exactly degenerate Schmidt multiplets: a max-bond-dim that cuts through one makes the kept subspace ambiguous (LAPACK's
+    own zgesvd and zgesdd then disagree at the 1e-3 level), so the truncated case uses a bond dimension that does not."""
+    n, p = 14, 2
+    circ = Cc.nearest_neighbor(Cc.qaoa_ring(n, p, seed=7))
+    edges = [(i, (i + 1) % n) for i in range(n)]
+    for chi, tol in ((0, EXACT_TOL), (20, TRUNC_TOL)):
+        e = tnqvm_b200.B200MPS(n, max_bond=chi)
+        e.run(circ)
+        o = O.OracleMPS(n, max_bond=chi).run(circ)
+        zz = e.expval_zz_pairs(edges)
+        ref = np.array([o.expval_z([i, j]) for i, j in edges])
+        assert np.abs(zz - ref).max() < tol, chi
+        assert abs(((1 - zz) / 2).sum() - ((1 - ref) / 2).sum()) < n * tol
+        assert abs(e.norm() - o.norm()) < tol
+        e.close()
+
+
+def test_config5_sycamore_style_amplitude_and_fidelity(O):
+    """BASELINE config 5 scaled to oracle size: Sycamore-style layers (fSim(pi/2, pi/6), sqrt rotations), SVD truncation
+    active; outputs are the amplitude of |0...0>, the norm and the fidelity estimate from the discarded weight."""
+    n, depth, chi = 12, 10, 16
+    circ = Cc.nearest_neighbor(Cc.sycamore_like(n, depth, seed=3))
+    e = tnqvm_b200.B200MPS(n, max_bond=chi)
+    e.run(circ)
+    o = O.OracleMPS(n, max_bond=chi).run(circ)
+    zero = [0] * n
+    assert abs(e.amplitude(zero) - o.amplitude(zero)) < TRUNC_TOL
+    some = [(k * 5) % 2 for k in range(n)]
+    assert abs(e.amplitude(some) - o.amplitude(some)) < TRUNC_TOL
+    assert abs(e.norm() - o.norm()) < TRUNC_TOL
+    dw, dwo = e.discarded_weight(), o.discarded_weight()
+    assert dwo > 1e-6 and abs(dw - dwo) < 1e-4 * max(1.0, dwo)
+    e.close()
