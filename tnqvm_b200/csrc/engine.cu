@@ -928,6 +928,7 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     if (const char* e = getenv("MPS_B200_JACOBI_TOL")) h->jacobi_tol = atof(e);
     if (const char* e = getenv("MPS_B200_NULL_TOL")) h->null_tol = atof(e);
     if (const char* e = getenv("MPS_B200_3M")) jacobi_set_3m(atoi(e));
+    if (const char* e = getenv("MPS_B200_SMALL_GEMM")) gemm_set_small_path(atoi(e));
     if (seed) h->rng.seed(seed);
     else { std::random_device rd; h->rng.seed(rd()); }   // RandomEngine.hpp:39-42
     h->reset_state();

@@ -245,6 +245,78 @@ __global__ void __launch_bounds__(NTHREADS, 2) zgemm_dmma_kernel1(const __grid_c
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// Small-problem variant for the transfer-matrix sweeps (one chi x chi environment times one site): a 64x64-tiled launch
+// of a 256 x 256 x 512 product is 16 CTAs on 148 SMs.  Here a CTA owns a 32x32 tile (4 warps, 16x16 complex each) and the
+// DMMA fragments are loaded straight from global memory (L2-resident operands, 64-128 byte segments), K unrolled by four
+// chunks so 16 loads are in flight per thread.  Plain products only: C = alpha * opA(A) * opB(B).
+template <int LAYOUT>
+__global__ void __launch_bounds__(128, 4) zgemm_small_kernel(const __grid_constant__ GemmProblem P) {
+  constexpr bool AK = (LAYOUT == 1);   // A given as K x M, used conj-transposed
+  constexpr bool BC = (LAYOUT == 2);   // B given as N x K, used conj-transposed
+  const int M = P.M, N = P.N, K = P.K;
+  const int tiles_m = (M + 31) / 32;
+  const int i0 = (blockIdx.x % tiles_m) * 32, j0 = (blockIdx.x / tiles_m) * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int m0 = i0 + (warp >> 1) * 16, n0 = j0 + (warp & 1) * 16;
+  const double2* __restrict__ A = P.A;
+  const double2* __restrict__ B = P.B;
+  const int lda = P.lda, ldb = P.ldb, bcs = P.b_col_stride, bco = P.b_col_off;
+  double cre[2][2][2], cim[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { cre[i][j][0] = cre[i][j][1] = cim[i][j][0] = cim[i][j][1] = 0.0; }
+  const double2 z = make_double2(0.0, 0.0);
+  constexpr int UN = 4;
+  for (int k0 = 0; k0 < K; k0 += 4 * UN) {
+    double2 a[UN][2], b[UN][2];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int k = k0 + 4 * u + lk;
+      const bool kok = k < K;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int m = m0 + 8 * i + lr;
+        a[u][i] = (kok && m < M) ? (AK ? A[k + (size_t)lda * m] : A[m + (size_t)lda * k]) : z;
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = n0 + 8 * j + lr;
+        b[u][j] = (kok && n < N) ? (BC ? B[n + (size_t)ldb * k] : B[k + (size_t)ldb * ((size_t)n * bcs + bco)]) : z;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double ar = a[u][i].x, ai = AK ? -a[u][i].y : a[u][i].y;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double br = b[u][j].x, bi = BC ? -b[u][j].y : b[u][j].y;
+          dmma884(cre[i][j][0], cre[i][j][1], ar, br);
+          dmma884(cre[i][j][0], cre[i][j][1], -ai, bi);
+          dmma884(cim[i][j][0], cim[i][j][1], ar, bi);
+          dmma884(cim[i][j][0], cim[i][j][1], ai, br);
+        }
+      }
+  }
+  const double alpha = P.alpha;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = m0 + 8 * i + lr;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = n0 + 8 * j + 2 * lk + e;
+        if (col < N) P.C[row + (size_t)P.ldc * col] = make_double2(alpha * cre[i][j][e], alpha * cim[i][j][e]);
+      }
+  }
+}
+
 int gemm_tiles(int M, int N, int mode) {
   const int tsz = mode ? 32 : 64;
   return ((M + tsz - 1) / tsz) * ((N + tsz - 1) / tsz);
@@ -262,9 +334,21 @@ static void set_attrs() {
   attr_set = true;
 }
 
+static bool g_small_gemm = true;
+void gemm_set_small_path(int on) { g_small_gemm = on != 0; }
+
 void launch_gemm1(const GemmProblem& p, int layout, cudaStream_t s) {
   const int tiles = gemm_tiles(p.M, p.N, p.mode);
   if (tiles <= 0) return;
+  // too few 64x64 tiles to fill the GPU: 32x32 tiles, fragments straight from L2
+  if (g_small_gemm && tiles < 120 && p.mode == 0 && !p.a_gather && !p.b_gather && !p.row_scale && !p.col_scale && !p.C2 && !p.conjT_out &&
+      (layout == 0 || (p.b_col_stride == 1 && p.b_col_off == 0))) {
+    const int t32 = ((p.M + 31) / 32) * ((p.N + 31) / 32);
+    if (layout == 0) zgemm_small_kernel<0><<<t32, 128, 0, s>>>(p);
+    else if (layout == 1) zgemm_small_kernel<1><<<t32, 128, 0, s>>>(p);
+    else zgemm_small_kernel<2><<<t32, 128, 0, s>>>(p);
+    return;
+  }
   set_attrs();
   dim3 grid(tiles, 1);
   if (layout == 0) zgemm_dmma_kernel1<0><<<grid, NTHREADS, SMEM_BYTES, s>>>(p);

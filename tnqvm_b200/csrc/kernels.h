@@ -33,6 +33,7 @@ struct GemmProblem {
 void launch_gemm(const GemmProblem* d_probs, int batch, int max_tiles, int layout, cudaStream_t s);
 void launch_gemm1(const GemmProblem& p, int layout, cudaStream_t s);   // one problem, descriptor by value
 int gemm_tiles(int M, int N, int mode);
+void gemm_set_small_path(int on);   // A/B switch for the 32x32-tile single-problem kernel (default on)
 
 // ---------------------------------------------------------------------------------------------
 // Batched blocked Householder QR, R factor only (qr_dmma.cu): Y (M x N, M >= N) is overwritten (R in its upper
