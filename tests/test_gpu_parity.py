@@ -105,8 +105,9 @@ def test_golden_fixtures_on_gpu():
 
 
 @pytest.mark.parametrize("opts", [dict(qr_prereduce=0), dict(jacobi_persistent=0), dict(jacobi_persistent=0, jacobi_groups=3),
-                                  dict(qr_prereduce=0, jacobi_persistent=0), dict(discard_margin=1e-12)],
-                         ids=["no_qr", "step_kernels", "stream_groups", "no_qr_step_kernels", "discard_rule"])
+                                  dict(qr_prereduce=0, jacobi_persistent=0), dict(discard_margin=1e-12), dict(qr_lookahead=1),
+                                  dict(jacobi_3m=1)],
+                         ids=["no_qr", "step_kernels", "stream_groups", "no_qr_step_kernels", "discard_rule", "qr_lookahead", "jacobi_3m"])
 def test_svd_engine_variants_agree_with_oracle(O, opts):
     """Every SVD configuration (QR pre-reduction on/off, persistent dataflow sweep vs one launch per step, stream groups,
     discard-aware rule) must give the reference's observables: exact run at 1e-10, truncated run at TRUNC_TOL."""
@@ -122,6 +123,8 @@ def test_svd_engine_variants_agree_with_oracle(O, opts):
         assert abs(e.expval_z([0, n - 1]) - o.expval_z([0, n - 1])) < tol
         if chi == 0:
             assert np.abs(e.statevector() - o.statevector()).max() < tol
+        if "jacobi_3m" in opts:
+            e.set_option("jacobi_3m", 0)   # process-wide switch: restore the default
         e.close()
 
 

@@ -118,6 +118,8 @@ struct mps_b200_handle {
   cudaEvent_t gev[NGROUP][GDEPTH] = {};
   cudaEvent_t gend[NGROUP] = {}, gstart = nullptr;
   int* pin_rem = nullptr;   // [NGROUP][GDEPTH] pinned
+  cudaEvent_t qev[4] = {};   // QR look-ahead (side stream = gstream[0], idle while the QR runs)
+  int qr_lookahead = 0;   // measured: the panel chain is the critical path, overlapping the trailing update buys nothing at chi=256
   // counters
   double n2q = 0, n1q = 0, nlayers = 0, nsweeps = 0, nlaunch = 0, ms_theta = 0, ms_svd = 0, ms_wb = 0, ms_qr = 0;
 
@@ -373,8 +375,8 @@ struct mps_b200_handle {
       d.oG = ws.reserve(sizeof(double2) * (size_t)d.Mj * d.Ng);
       if (use_qr) {
         d.oY = ws.reserve(sizeof(double2) * (size_t)d.Mg * d.Ng);
-        d.oV = ws.reserve(sizeof(double2) * (size_t)d.Mg * QR_PB);
-        d.oTq = ws.reserve(sizeof(double2) * QR_PB * QR_PB);
+        d.oV = ws.reserve(sizeof(double2) * 2 * (size_t)d.Mg * QR_PB);
+        d.oTq = ws.reserve(sizeof(double2) * 2 * QR_PB * QR_PB);
       }
     }
     const size_t total = ws.off;
@@ -449,7 +451,7 @@ struct mps_b200_handle {
 
     // ---- QR pre-reduction: theta_o = Q R, the Jacobi runs on G = R^H
     if (use_qr) {
-      launch_qr((const QrProblem*)(wb + oQr), B, maxMg, maxNg, stream);
+      launch_qr((const QrProblem*)(wb + oQr), B, maxMg, maxNg, stream, qr_lookahead ? gstream[0] : nullptr, qr_lookahead ? qev : nullptr);
       nlaunch += qr_launch_count(maxNg);
       CK(cudaGetLastError());
     }
@@ -909,6 +911,7 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
       CK(cudaEventCreateWithFlags(&h->gend[g], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&h->gstart, cudaEventDisableTiming));
+    for (auto& ev : h->qev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CK(cudaMallocHost(&h->pin_rem, sizeof(int) * mps_b200_handle::NGROUP * mps_b200_handle::GDEPTH));
     h->sites.resize(h->ntot);
     h->norm_ver.assign(h->nreg, 0);
@@ -928,6 +931,7 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     if (const char* e = getenv("MPS_B200_JACOBI_TOL")) h->jacobi_tol = atof(e);
     if (const char* e = getenv("MPS_B200_NULL_TOL")) h->null_tol = atof(e);
     if (const char* e = getenv("MPS_B200_3M")) jacobi_set_3m(atoi(e));
+    if (const char* e = getenv("MPS_B200_QR_LOOKAHEAD")) h->qr_lookahead = atoi(e) != 0;
     if (const char* e = getenv("MPS_B200_SMALL_GEMM")) gemm_set_small_path(atoi(e));
     if (seed) h->rng.seed(seed);
     else { std::random_device rd; h->rng.seed(rd()); }   // RandomEngine.hpp:39-42
@@ -957,6 +961,7 @@ int mps_destroy(mps_handle_t h) {
     if (h->gend[g]) cudaEventDestroy(h->gend[g]);
   }
   if (h->gstart) cudaEventDestroy(h->gstart);
+  for (auto& ev : h->qev) if (ev) cudaEventDestroy(ev);
   if (h->pin_rem) cudaFreeHost(h->pin_rem);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -983,6 +988,7 @@ int mps_set_option(mps_handle_t h, const char* key, double value) {
   else if (k == "jacobi_persistent") { h->flush(); h->jacobi_persistent = value != 0; }
   else if (k == "discard_margin") { h->flush(); h->discard_margin = value; }
   else if (k == "jacobi_3m") { h->flush(); jacobi_set_3m(value != 0); }
+  else if (k == "qr_lookahead") { h->flush(); h->qr_lookahead = value != 0; }
   else if (k == "max_bond") h->max_bond = value > 0 ? (int)value : INT_MAX - 1;
   else if (k == "svd_cutoff") h->cutoff = value >= 0 ? value : DBL_MIN;
   else if (k == "gauge") h->gauge = (int)value;

@@ -37,7 +37,8 @@ void gemm_set_small_path(int on);   // A/B switch for the 32x32-tile single-prob
 
 // ---------------------------------------------------------------------------------------------
 // Batched blocked Householder QR, R factor only (qr_dmma.cu): Y (M x N, M >= N) is overwritten (R in its upper
-// triangle), G (N x N, ld = N) receives R^H.  V (M x QR_PB) and T (QR_PB x QR_PB) are per-matrix scratch.
+// triangle), G (N x N, ld = N) receives R^H.  V (2 x M x QR_PB) and T (2 x QR_PB x QR_PB) are per-matrix scratch
+// (double-buffered over consecutive panels).
 constexpr int QR_PB = 16;
 struct QrProblem {
   double2* Y;
@@ -46,7 +47,8 @@ struct QrProblem {
   double2* G;
   int M, N, ldy;
 };
-void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaStream_t s);
+// side/ev (4 timing-disabled events) enable the two-stream look-ahead schedule; pass nullptr for a single stream
+void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaStream_t s, cudaStream_t side, cudaEvent_t* ev);
 int qr_launch_count(int max_n);
 
 // ---------------------------------------------------------------------------------------------

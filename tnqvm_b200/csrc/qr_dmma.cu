@@ -204,7 +204,9 @@ __global__ void __launch_bounds__(PT, 1) qr_panel_kernel(const QrProblem* __rest
     }
   }
   __syncthreads();
-  for (int i = tid; i < PB * PB; i += PT) P.T[i] = sT[i % PB][i / PB];   // column-major PB x PB
+  double2* Tout = P.T + (size_t)(k & 1) * PB * PB;          // V and T are double-buffered: the trailing update of panel k
+  double2* Vout = P.V + (size_t)(k & 1) * P.M * PB;         // may still be running while panel k+1 is factored
+  for (int i = tid; i < PB * PB; i += PT) Tout[i] = sT[i % PB][i / PB];   // column-major PB x PB
   // clean reflector block for the update kernel: V (mk x PB, ld = P.M), unit diagonal, zeros above and beyond pw;
   // and the panel itself back to global memory
   {
@@ -218,23 +220,27 @@ __global__ void __launch_bounds__(PT, 1) qr_panel_kernel(const QrProblem* __rest
         if (i == c) v = make_double2(1.0, 0.0);
         else if (i > c) v = cmul(x, s_inv[c]);
       }
-      P.V[i + (size_t)P.M * c] = v;
+      Vout[i + (size_t)P.M * c] = v;
     }
   }
 }
 
 // C <- C - V * (T^H * (V^H C)) on a slab of SLAB trailing columns
-__global__ void __launch_bounds__(UT, 4) qr_update_kernel(const QrProblem* __restrict__ probs, int k) {
+// trailing columns [t0 + lo, t0 + hi) only (t0 = first column after the panel): the look-ahead schedule updates the next
+// panel's columns (lo = 0, hi = PB) ahead of the rest (lo = PB, hi = inf)
+__global__ void __launch_bounds__(UT, 4) qr_update_kernel(const QrProblem* __restrict__ probs, int k, int lo, int hi) {
   const QrProblem P = probs[blockIdx.y];
   const int c0 = k * PB;
   if (c0 >= P.N) return;
   const int pw = min(PB, P.N - c0);
   const int t0 = c0 + pw;
-  const int col0 = t0 + blockIdx.x * SLAB;
-  if (col0 >= P.N) return;
-  const int ncol = min(SLAB, P.N - col0);
+  const int col0 = t0 + lo + blockIdx.x * SLAB;
+  const int cend = (int)min((long)P.N, (long)t0 + hi);
+  if (col0 >= cend) return;
+  const int ncol = min(SLAB, cend - col0);
   const int r0 = c0, mk = P.M - r0;
-  const double2* __restrict__ V = P.V;
+  const double2* __restrict__ V = P.V + (size_t)(k & 1) * P.M * PB;
+  const double2* __restrict__ Tk = P.T + (size_t)(k & 1) * PB * PB;
   const int ldv = P.M, ldy = P.ldy;
   double2* C = P.Y + r0 + (size_t)ldy * col0;
 
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(UT, 4) qr_update_kernel(const QrProblem* __res
   __shared__ double2 sTm[PB][PB + 1];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lk = lane & 3;
-  for (int i = tid; i < PB * PB; i += UT) sTm[i % PB][i / PB] = P.T[i];
+  for (int i = tid; i < PB * PB; i += UT) sTm[i % PB][i / PB] = Tk[i];
 
   // ---------------- phase 1: W = V^H C  (PB x SLAB), K = mk rows split over the warps
   {
@@ -362,7 +368,12 @@ __global__ void __launch_bounds__(256) qr_rh_kernel(const QrProblem* __restrict_
 
 }  // namespace
 
-void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaStream_t s) {
+// Look-ahead schedule on two streams: the main stream factors panel k+1 as soon as its 16 columns have seen update k, while
+// the side stream applies update k to the rest of the trailing matrix:
+//   main: panel(k) -> [wait rest(k-1)] -> update(k, next panel's columns) -> panel(k+1) ...
+//   side: [wait panel(k)] -> update(k, the rest)
+// `ev` must hold 4 events (timing disabled).
+void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaStream_t s, cudaStream_t side, cudaEvent_t* ev) {
   if (batch <= 0 || max_n <= 0) return;
   // the panel is staged in shared memory whenever it fits (the kernel applies the same test per matrix)
   const size_t want = (size_t)max_m * PB * sizeof(double2);
@@ -373,20 +384,40 @@ void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaSt
     attr_set = true;
   }
   const int npanels = (max_n + PB - 1) / PB;
+  const bool two = side != nullptr && ev != nullptr && npanels > 2;
+  if (two) {   // the side stream starts behind everything already queued on the main stream
+    cudaEventRecord(ev[2], s);
+    cudaStreamWaitEvent(side, ev[2], 0);
+  }
   for (int k = 0; k < npanels; ++k) {
     qr_panel_kernel<<<batch, PT, smem, s>>>(d_probs, k);
     const int ntr = max_n - (k + 1) * PB;
-    if (ntr > 0) {
+    if (ntr <= 0) break;
+    if (!two) {
       dim3 grid((ntr + SLAB - 1) / SLAB, batch);
-      qr_update_kernel<<<grid, UT, 0, s>>>(d_probs, k);
+      qr_update_kernel<<<grid, UT, 0, s>>>(d_probs, k, 0, 1 << 30);
+      continue;
     }
+    cudaEventRecord(ev[0], s);                       // panel k done
+    if (ntr > PB) {
+      cudaStreamWaitEvent(side, ev[0], 0);
+      dim3 grid((ntr - PB + SLAB - 1) / SLAB, batch);
+      qr_update_kernel<<<grid, UT, 0, side>>>(d_probs, k, PB, 1 << 30);
+    }
+    if (k > 0) cudaStreamWaitEvent(s, ev[1], 0);     // rest(k-1) done: the next panel's columns are current up to step k-1
+    if (ntr > PB) cudaEventRecord(ev[1], side);      // rest(k) done
+    qr_update_kernel<<<dim3(1, batch), UT, 0, s>>>(d_probs, k, 0, PB);
+  }
+  if (two) {
+    cudaEventRecord(ev[3], side);
+    cudaStreamWaitEvent(s, ev[3], 0);
   }
   dim3 g2((max_n + 31) / 32, (max_n + 31) / 32, batch);
   qr_rh_kernel<<<g2, 256, 0, s>>>(d_probs);
 }
 int qr_launch_count(int max_n) {
   const int npanels = (max_n + PB - 1) / PB;
-  return 2 * npanels;   // panels + updates (the last panel has no update) + the R^H transpose
+  return 3 * npanels - 2;   // panels + look-ahead and trailing updates (the last panel has none) + the R^H transpose
 }
 
 }  // namespace mpsb200
