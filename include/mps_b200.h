@@ -54,6 +54,10 @@ int mps_apply_1q(mps_handle_t h, int q, const double m[8]);
 int mps_apply_2q(mps_handle_t h, int q0, int q1, const double m[32]);
 /* count independent (or not: dependencies are resolved) 2q gates in one call */
 int mps_apply_layer(mps_handle_t h, int count, const int* q0, const int* q1, const double* mats);
+/* a whole instruction list in one call (what TNQVM::execute's InstructionIterator loop delivers, TNQVM.cpp:126-134):
+ * gate i acts on q0[i] (and q1[i], or -1 for a single-qubit gate); mats holds 32 doubles per gate, a row-major 4x4 complex
+ * matrix or a row-major 2x2 in the first 8 */
+int mps_apply_gates(mps_handle_t h, int count, const int* q0, const int* q1, const double* mats);
 /* gates are queued and executed in dependency layers; flush forces execution, sync also waits */
 int mps_flush(mps_handle_t h);
 int mps_sync(mps_handle_t h);

@@ -360,3 +360,15 @@ def test_config5_sycamore_style_amplitude_and_fidelity(O):
     dw, dwo = e.discarded_weight(), o.discarded_weight()
     assert dwo > 1e-6 and abs(dw - dwo) < 1e-4 * max(1.0, dwo)
     e.close()
+
+
+def test_compiled_circuit_equals_gate_by_gate(O):
+    """mps_apply_gates (one ABI call per instruction list) against the per-gate entry points, Swap bit order included."""
+    n = 10
+    circ = Cc.brickwork(n, 6, seed=31) + [("Swap", (3, 4), ()), ("Swap", (6, 5), ()), ("fSim", (8, 7), (0.3, 0.2)), ("Measure", (2,), ())]
+    a = tnqvm_b200.B200MPS(n).run(circ)
+    b = tnqvm_b200.B200MPS(n).run(tnqvm_b200.CompiledCircuit(circ))
+    assert np.abs(a.statevector() - b.statevector()).max() < 1e-13
+    o = O.OracleMPS(n).run(circ)
+    assert np.abs(b.statevector() - o.statevector()).max() < EXACT_TOL
+    a.close(); b.close()

@@ -23,6 +23,7 @@ SYMBOLS = {
     "mps_apply_1q": ([C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     "mps_apply_2q": ([C.c_void_p, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "mps_apply_layer": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "mps_apply_gates": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "mps_flush": ([C.c_void_p], C.c_int),
     "mps_sync": ([C.c_void_p], C.c_int),
     "mps_norm": ([C.c_void_p, C.c_int, C.POINTER(C.c_double)], C.c_int),

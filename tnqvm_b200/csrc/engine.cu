@@ -159,13 +159,14 @@ struct mps_b200_handle {
       size_t ncap = need;
       // grow geometrically but never beyond what max_bond allows
       if (max_bond < (1 << 20)) ncap = std::max(need, std::min((size_t)2 * max_bond * max_bond, need * 2));
+      // stream-ordered allocation from the device's default pool (kept warm, see mps_create): growing a site costs
+      // microseconds and no synchronisation, which matters while the bonds of a fresh |0...0> state double gate by gate
       double2* nd = nullptr;
-      CK(cudaMalloc(&nd, ncap * sizeof(double2)));
+      CK(cudaMallocAsync((void**)&nd, ncap * sizeof(double2), stream));
       if (s.d) {
         if (keep_data)
           CK(cudaMemcpyAsync(nd, s.d, (size_t)2 * s.dl * s.dr * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
-        CK(cudaStreamSynchronize(stream));
-        CK(cudaFree(s.d));
+        CK(cudaFreeAsync(s.d, stream));
       }
       s.d = nd;
       s.cap = ncap;
@@ -904,6 +905,12 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     if (svd_cutoff >= 0) h->cutoff = svd_cutoff;
     h->gauge = gauge; h->device = device;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {
+      cudaMemPool_t pool;
+      CK(cudaDeviceGetDefaultMemPool(&pool, device));
+      uint64_t keep = UINT64_MAX;   // never hand freed site buffers back to the driver between gates
+      CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
     for (int g = 0; g < mps_b200_handle::NGROUP; ++g) {
       CK(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
@@ -950,7 +957,8 @@ int mps_destroy(mps_handle_t h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   if (getenv("MPS_B200_DBG_MODE")) jacobi_print_phase_timing();
-  for (auto& s : h->sites) if (s.d) cudaFree(s.d);
+  for (auto& s : h->sites) if (s.d) cudaFreeAsync(s.d, h->stream);
+  cudaStreamSynchronize(h->stream);
   if (h->ws.base) cudaFree(h->ws.base);
   for (int i = 0; i < 2; ++i) if (h->pin[i]) cudaFreeHost(h->pin[i]);
   if (h->pin_rb) cudaFreeHost(h->pin_rb);
@@ -1005,6 +1013,15 @@ int mps_apply_2q(mps_handle_t h, int q0, int q1, const double m[32]) {
 int mps_apply_layer(mps_handle_t h, int count, const int* q0, const int* q1, const double* mats) {
   API_BEGIN(h)
   for (int i = 0; i < count; ++i) h->push_2q(q0[i], q1[i], reinterpret_cast<const cplx*>(mats + 32 * (size_t)i));
+  API_END(h)
+}
+int mps_apply_gates(mps_handle_t h, int count, const int* q0, const int* q1, const double* mats) {
+  API_BEGIN(h)
+  for (int i = 0; i < count; ++i) {
+    const cplx* m = reinterpret_cast<const cplx*>(mats + 32 * (size_t)i);
+    if (q1[i] < 0) h->push_1q(q0[i], m);
+    else h->push_2q(q0[i], q1[i], m);
+  }
   API_END(h)
 }
 int mps_flush(mps_handle_t h) { API_BEGIN(h) h->flush(); API_END(h) }

@@ -10,6 +10,36 @@ from .gates import gate_matrix
 GAUGE_REFERENCE, GAUGE_LEFT, GAUGE_RIGHT = 0, 1, 2
 
 
+class CompiledCircuit:
+    """A circuit lowered once to the arrays mps_apply_gates takes: the gate-name -> matrix step of the visitor
+    (ExatnUtils.cpp:36-133) done ahead of time, visit(Swap)'s bit sort (:1030-1033) included."""
+
+    def __init__(self, circuit, offset=0):
+        q0, q1, mats, self.measure = [], [], [], []
+        for g in circuit:
+            name, qs = g[0], g[1]
+            if name == "Measure":
+                self.measure.append(qs[0])
+                continue
+            if name == "I":
+                continue
+            m = gate_matrix(name, g[2] if len(g) > 2 else ())
+            buf = np.zeros(16, dtype=np.complex128)
+            if m.shape[0] == 2:
+                buf[:4] = m.reshape(-1)
+                q0.append(qs[0] + offset); q1.append(-1)
+            else:
+                if name == "Swap" and qs[0] < qs[1]:
+                    qs = (qs[1], qs[0])
+                buf[:] = m.reshape(-1)
+                q0.append(qs[0] + offset); q1.append(qs[1] + offset)
+            mats.append(buf)
+        self.count = len(q0)
+        self.q0 = np.ascontiguousarray(q0, dtype=np.int32)
+        self.q1 = np.ascontiguousarray(q1, dtype=np.int32)
+        self.mats = np.ascontiguousarray(mats, dtype=np.complex128).reshape(-1) if mats else np.zeros(0, dtype=np.complex128)
+
+
 class B200MPS:
     def __init__(self, n_qubits, max_bond=0, svd_cutoff=-1.0, gauge=GAUGE_REFERENCE, device=0, seed=0, n_registers=1,
                  **options):
@@ -79,9 +109,19 @@ class B200MPS:
             self.apply_2q(qubits[0], qubits[1], m)
 
     def run(self, circuit, offset=0):
+        if isinstance(circuit, CompiledCircuit):
+            return self.run_compiled(circuit)
         for g in circuit:
             qs = tuple(q + offset for q in g[1]) if g[0] != "Measure" else g[1]
             self.apply(g[0], qs, g[2] if len(g) > 2 else ())
+        return self
+
+    def run_compiled(self, cc):
+        """One ABI call for a whole instruction list (mps_apply_gates)."""
+        if cc.count:
+            self._ck(self.L.mps_apply_gates(self.h, cc.count, cc.q0.ctypes.data, cc.q1.ctypes.data, cc.mats.ctypes.data))
+        for q in cc.measure:
+            self._ck(self.L.mps_measure(self.h, q))
         return self
 
     def flush(self):
