@@ -269,7 +269,7 @@ def test_full_size_properties(chi):
     e.close()
 
 
-@pytest.mark.parametrize("chi,gauge", [(256, 0), (256, 1), (96, 2), (320, 0)])
+@pytest.mark.parametrize("chi,gauge", [(256, 0), (256, 1), (96, 2), (320, 0), (1024, 0)])
 def test_full_size_truncated_gate_against_lapack(chi, gauge):
     """One saturated-bond gate at BASELINE size with truncation 2 chi -> chi active, checked against LAPACK (numpy) on the same
     theta: retained singular values, discarded weight, and the product of the two new sites = the best rank-chi approximation
