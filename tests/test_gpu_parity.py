@@ -106,8 +106,9 @@ def test_golden_fixtures_on_gpu():
 
 @pytest.mark.parametrize("opts", [dict(qr_prereduce=0), dict(jacobi_persistent=0), dict(jacobi_persistent=0, jacobi_groups=3),
                                   dict(qr_prereduce=0, jacobi_persistent=0), dict(discard_margin=1e-12), dict(qr_lookahead=1),
-                                  dict(jacobi_3m=1)],
-                         ids=["no_qr", "step_kernels", "stream_groups", "no_qr_step_kernels", "discard_rule", "qr_lookahead", "jacobi_3m"])
+                                  dict(jacobi_3m=1), dict(jacobi_block16=1)],
+                         ids=["no_qr", "step_kernels", "stream_groups", "no_qr_step_kernels", "discard_rule", "qr_lookahead", "jacobi_3m",
+                              "block16"])
 def test_svd_engine_variants_agree_with_oracle(O, opts):
     """Every SVD configuration (QR pre-reduction on/off, persistent dataflow sweep vs one launch per step, stream groups,
     discard-aware rule) must give the reference's observables: exact run at 1e-10, truncated run at TRUNC_TOL."""

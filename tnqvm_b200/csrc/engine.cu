@@ -113,6 +113,7 @@ struct mps_b200_handle {
   int jacobi_persistent = 1;   // one persistent dataflow launch per sweep (jacobi_sweep_kernel) instead of one launch per step
   int sm_count = 148;
   int stagger_ns = 0;
+  int block16 = 0;   // Jacobi over 16-column blocks (32-column tasks): half the passes through L2 per sweep
   double discard_margin = 0.0;    // discard-aware rotation rule: fraction of the keep-th largest squared column norm (0 = off)
   cudaStream_t gstream[NGROUP] = {};
   cudaEvent_t gev[NGROUP][GDEPTH] = {};
@@ -363,7 +364,7 @@ struct mps_b200_handle {
     for (int b = 0; b < B; ++b) {
       Dim& d = D[b];
       d.oCn2 = ws.reserve(sizeof(double) * d.Ng);
-      d.oWd = ws.reserve(sizeof(double2) * 64 * (size_t)((d.Ng + 7) / 8));
+      d.oWd = ws.reserve(sizeof(double2) * 256 * (size_t)((d.Ng + 15) / 16));   // >= 64 per 8-column block as well
       {
         const size_t nbe_ = (size_t)((((d.Ng + 7) / 8) + 1) & ~1);
         d.oVer = ws.reserve(sizeof(int) * nbe_ + 8 + sizeof(int2) * nbe_ * nbe_);   // versions, then the clean-pair memo
@@ -419,7 +420,8 @@ struct mps_b200_handle {
         q.Y = (double2*)(wb + d.oY); q.V = (double2*)(wb + d.oV); q.T = (double2*)(wb + d.oTq); q.G = j.G;
         q.M = d.Mg; q.N = d.Ng; q.ldy = d.Mg;
       }
-      j.nb = (d.Ng + 7) / 8;
+      const bool b16 = block16 && jacobi_persistent && NG == 1;
+      j.nb = b16 ? (d.Ng + 15) / 16 : (d.Ng + 7) / 8;
       j.nbe = (j.nb == 1) ? 1 : ((j.nb + 1) & ~1);
       j.cn2 = (double*)(wb + d.oCn2); j.thr = (double*)(wb + oThr) + b; j.wd = (double2*)(wb + d.oWd);
       {
@@ -474,6 +476,10 @@ struct mps_b200_handle {
       int* d_cnt = d_prog + (size_t)B * pstride;
       if (trace) CK(cudaEventRecord(ev[5], stream));
       for (; sweep < max_sweeps; ++sweep) {
+        if (block16)
+          launch_jacobi_sweep16((const JacobiProblem*)(wb + oJac), B, max_pairs, max_steps, sweep * max_steps, tol2, dead2, d_fro2,
+                                d_dirty, d_done, d_prog, pstride, d_cnt + sweep, d_rem + 1, sm_count, stream);
+        else
         launch_jacobi_sweep((const JacobiProblem*)(wb + oJac), B, max_pairs, max_steps, sweep * max_steps, tol2, dead2, d_fro2, d_dirty,
                             d_done, d_prog, pstride, d_cnt + sweep, d_rem + 1, sm_count * 4, stagger_ns, stream);
         launch_jacobi_check(B, d_dirty, d_done, d_rem, stream);
@@ -939,6 +945,7 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     if (const char* e = getenv("MPS_B200_NULL_TOL")) h->null_tol = atof(e);
     if (const char* e = getenv("MPS_B200_3M")) jacobi_set_3m(atoi(e));
     if (const char* e = getenv("MPS_B200_QR_LOOKAHEAD")) h->qr_lookahead = atoi(e) != 0;
+    if (const char* e = getenv("MPS_B200_BLOCK16")) h->block16 = atoi(e) != 0;
     if (const char* e = getenv("MPS_B200_SMALL_GEMM")) gemm_set_small_path(atoi(e));
     if (seed) h->rng.seed(seed);
     else { std::random_device rd; h->rng.seed(rd()); }   // RandomEngine.hpp:39-42
@@ -997,6 +1004,7 @@ int mps_set_option(mps_handle_t h, const char* key, double value) {
   else if (k == "discard_margin") { h->flush(); h->discard_margin = value; }
   else if (k == "jacobi_3m") { h->flush(); jacobi_set_3m(value != 0); }
   else if (k == "qr_lookahead") { h->flush(); h->qr_lookahead = value != 0; }
+  else if (k == "jacobi_block16") { h->flush(); h->block16 = value != 0; }
   else if (k == "max_bond") h->max_bond = value > 0 ? (int)value : INT_MAX - 1;
   else if (k == "svd_cutoff") h->cutoff = value >= 0 ? value : DBL_MIN;
   else if (k == "gauge") h->gauge = (int)value;

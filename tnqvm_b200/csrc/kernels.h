@@ -76,6 +76,10 @@ void launch_jacobi_step(const JacobiProblem* d_probs, int batch, int max_pairs, 
 void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
                          const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
                          int* d_fault, int grid_ctas, int stagger_ns, cudaStream_t s);   // *d_fault += 1 if a dependency wait timed out
+// the same sweep over 16-column blocks (JacobiProblem.nb / nbe count 16-column blocks, wd holds 256 complex per block)
+void launch_jacobi_sweep16(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
+                           const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
+                           int* d_fault, int n_sm, cudaStream_t s);
 void jacobi_set_debug_mode(int mode);   // timing experiments only
 void jacobi_print_phase_timing();
 void jacobi_set_3m(int on);   // 3M complex product in the column update (default off); process-wide
