@@ -44,8 +44,12 @@ int mps_destroy(mps_handle_t h);
 const char* mps_last_error(mps_handle_t h); /* h may be NULL: last mps_create error */
 int mps_reset(mps_handle_t h);              /* back to |0...0>, ExaTnMpsVisitor.cpp:273-326 */
 
-/* keys: "cutoff_on_sqrt" (computePartialNormsSync ambiguity), "fuse_1q", "renormalize",
- * "jacobi_tol", "jacobi_max_sweeps", "profile", "layer_batch" (0 = execute gate by gate) */
+/* keys: "max_bond", "svd_cutoff", "gauge" (as in mps_create), "cutoff_on_sqrt" (computePartialNormsSync ambiguity,
+ * SURVEY 8c), "fuse_1q", "renormalize", "jacobi_tol", "null_tol", "jacobi_max_sweeps", "profile", "layer_batch" (0 = execute
+ * gate by gate).  Engine variants kept for A/B measurements, all parity-tested (tests/test_gpu_parity.py): "qr_prereduce"
+ * (default 1), "jacobi_persistent" (1: one dataflow launch per sweep; 0: one launch per tournament step), "jacobi_groups"
+ * (stream groups of the per-step path), "jacobi_block16" (0: 8-column blocks; 1: 16-column blocks), "jacobi_3m" (0; process
+ * wide), "discard_margin" (0 = off), "qr_lookahead" (0). */
 int mps_set_option(mps_handle_t h, const char* key, double value);
 
 /* applyGate 1q branch, ExaTnMpsVisitor.cpp:1185-1292.  m = row-major 2x2 complex. */
