@@ -45,11 +45,14 @@ const char* mps_last_error(mps_handle_t h); /* h may be NULL: last mps_create er
 int mps_reset(mps_handle_t h);              /* back to |0...0>, ExaTnMpsVisitor.cpp:273-326 */
 
 /* keys: "max_bond", "svd_cutoff", "gauge" (as in mps_create), "cutoff_on_sqrt" (computePartialNormsSync ambiguity,
- * SURVEY 8c), "fuse_1q", "renormalize", "jacobi_tol", "null_tol", "jacobi_max_sweeps", "profile", "layer_batch" (0 = execute
+ * SURVEY 8c), "fuse_1q", "fuse_2q" (default 0: merge consecutive 2q gates on one site pair into one 4x4 -- fewer SVDs, but with
+ * truncation active no longer truncation-for-truncation identical to the reference), "renormalize", "jacobi_tol", "null_tol", "jacobi_max_sweeps", "profile", "layer_batch" (0 = execute
  * gate by gate).  Engine variants kept for A/B measurements, all parity-tested (tests/test_gpu_parity.py): "qr_prereduce"
  * (default 1), "jacobi_persistent" (1: one dataflow launch per sweep; 0: one launch per tournament step), "jacobi_groups"
  * (stream groups of the per-step path), "jacobi_block16" (0: 8-column blocks; 1: 16-column blocks), "jacobi_3m" (0; process
- * wide), "discard_margin" (0 = off), "qr_lookahead" (0). */
+ * wide), "discard_margin" (0 = off), "qr_lookahead" (0), "jacobi_ctas_per_sm" (0 = by load: as many resident CTAs of the
+ * persistent sweep kernel as a tournament step has pair tasks, 1..4 per SM), "jacobi_wide_tasks" (1: eight warps per pair task
+ * when at most two tasks per SM are resident, the few-gates-per-layer regime of routed circuits; 0: always four). */
 int mps_set_option(mps_handle_t h, const char* key, double value);
 
 /* applyGate 1q branch, ExaTnMpsVisitor.cpp:1185-1292.  m = row-major 2x2 complex. */
@@ -103,7 +106,8 @@ int mps_resize_site(mps_handle_t h, int k, int dl, int dr, void** dptr);
 
 /* counters: [0] 2q gates executed, [1] 1q kernel gates, [2] layers, [3] jacobi sweeps, [4] kernel launches,
  * [5] ms merge GEMM, [6] ms SVD (QR pre-reduction + Jacobi), [7] ms truncate+write-back, [8] ms of [6] spent in the QR
- * pre-reduction (5..8 only with option "profile"), [9] real flops issued on the DMMA pipe by the Jacobi pair tasks (process-wide) */
+ * pre-reduction (5..8 only with option "profile"), [9] real flops issued on the DMMA pipe by the Jacobi pair tasks (process-wide),
+ * [10] 2q gates merged into their predecessor on the same site pair (option "fuse_2q") */
 int mps_stats(mps_handle_t h, double* out, int cap);
 /* the CUDA stream (cudaStream_t) all work of this handle is issued on: callers time with events recorded on it
  * and order their own transfers (NCCL send/recv of boundary sites) against it */

@@ -106,9 +106,10 @@ def test_golden_fixtures_on_gpu():
 
 @pytest.mark.parametrize("opts", [dict(qr_prereduce=0), dict(jacobi_persistent=0), dict(jacobi_persistent=0, jacobi_groups=3),
                                   dict(qr_prereduce=0, jacobi_persistent=0), dict(discard_margin=1e-12), dict(qr_lookahead=1),
-                                  dict(jacobi_3m=1), dict(jacobi_block16=1)],
+                                  dict(jacobi_3m=1), dict(jacobi_block16=1), dict(jacobi_wide_tasks=0, jacobi_ctas_per_sm=4),
+                                  dict(jacobi_wide_tasks=1, jacobi_ctas_per_sm=2), dict(jacobi_wide_tasks=0, jacobi_ctas_per_sm=1)],
                          ids=["no_qr", "step_kernels", "stream_groups", "no_qr_step_kernels", "discard_rule", "qr_lookahead", "jacobi_3m",
-                              "block16"])
+                              "block16", "narrow_tasks_4_per_sm", "wide_tasks_2_per_sm", "narrow_tasks_1_per_sm"])
 def test_svd_engine_variants_agree_with_oracle(O, opts):
     """Every SVD configuration (QR pre-reduction on/off, persistent dataflow sweep vs one launch per step, stream groups,
     discard-aware rule) must give the reference's observables: exact run at 1e-10, truncated run at TRUNC_TOL."""
@@ -372,4 +373,35 @@ def test_compiled_circuit_equals_gate_by_gate(O):
     assert np.abs(a.statevector() - b.statevector()).max() < 1e-13
     o = O.OracleMPS(n).run(circ)
     assert np.abs(b.statevector() - o.statevector()).max() < EXACT_TOL
+    a.close(); b.close()
+
+
+def test_fuse_2q_merges_same_pair_gates_and_stays_exact(O):
+    """Option fuse_2q: CX.Rz.CX on one site pair becomes one 4x4, Swap.Swap between two routed gates
+    disappears, in either qubit order and with 1q gates folded in between.  Without truncation the state must equal the
+    oracle's (which, like the reference, applies every gate separately, ExaTnMpsVisitor.cpp:1394-1630)."""
+    n = 10
+    circ = Cc.nearest_neighbor(Cc.qaoa_ring(n, 2, seed=11))
+    circ += [("CNOT", (4, 3), ()), ("Ry", (3,), (0.37,)), ("fSim", (3, 4), (0.4, 0.9)), ("H", (4,), ()), ("CZ", (4, 3), ()),
+             ("Swap", (6, 7), ()), ("Swap", (7, 6), ()), ("CNOT", (6, 7), ()), ("CNOT", (7, 8), ()), ("CNOT", (6, 7), ())]
+    o = O.OracleMPS(n).run(circ)
+    ref = o.statevector()
+    n2 = Cc.count_gates(circ)[1]
+    for compiled in (False, True):
+        e = tnqvm_b200.B200MPS(n, fuse_2q=1)
+        e.run(tnqvm_b200.CompiledCircuit(circ) if compiled else circ)
+        st = e.stats()
+        assert np.abs(e.statevector() - ref).max() < EXACT_TOL
+        # 9 chain edges per QAOA layer (CX.Rz.CX -> one gate) + the four merges of the tail above
+        assert st["gates_2q_fused"] >= 22 and st["gates_2q"] + st["gates_2q_fused"] <= n2   # identity products are dropped
+        e.close()
+    # truncation active: the fused run truncates at fewer points, so it is no longer truncation-for-truncation the reference
+    # run (why the option is off by default), but it must stay as close to the exact state as the gate-by-gate run is
+    chi = 8
+    a = tnqvm_b200.B200MPS(n, max_bond=chi).run(circ)
+    b = tnqvm_b200.B200MPS(n, max_bond=chi, fuse_2q=1).run(circ)
+    sa, sb = a.statevector(), b.statevector()
+    fa = abs(np.vdot(ref, sa)) ** 2 / np.vdot(sa, sa).real
+    fb = abs(np.vdot(ref, sb)) ** 2 / np.vdot(sb, sb).real
+    assert fa > 0.9 and fb >= fa - 5e-3
     a.close(); b.close()

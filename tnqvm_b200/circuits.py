@@ -112,6 +112,43 @@ def sycamore_like(n, depth, seed=3):
     return c
 
 
+def sycamore_grid(depth=14, rows=9, cols=6, n=53, seed=0):
+    """C5 at full shape without the reference's resource file (absent on the GPU box): a 53-qubit 2D random circuit in the
+    style of examples/sycamore/resources/sycamore_53_14_0.xasm -- per cycle one of sqrt-X / sqrt-Y / sqrt-W on every qubit
+    (never the same gate twice in a row on a qubit), then fSim(theta ~ pi/2, phi ~ pi/6) with per-coupler angles on one of
+    the four coupler patterns in the order ABCDCDAB.  Qubits are numbered row-major on a rows x cols grid, so the horizontal
+    couplers are nearest neighbours and the vertical ones are `cols` apart (the resource file has distances 1..10);
+    nearest_neighbor() routes them exactly as TNQVM's pass would."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    idx = lambda r, c_: r * cols + c_
+    pat = {"A": [(idx(r, c_), idx(r, c_ + 1)) for r in range(rows) for c_ in range(0, cols - 1, 2)],
+           "B": [(idx(r, c_), idx(r, c_ + 1)) for r in range(rows) for c_ in range(1, cols - 1, 2)],
+           "C": [(idx(r, c_), idx(r + 1, c_)) for r in range(0, rows - 1, 2) for c_ in range(cols)],
+           "D": [(idx(r, c_), idx(r + 1, c_)) for r in range(1, rows - 1, 2) for c_ in range(cols)]}
+    angles = {}
+    for k in "ABCD":
+        pat[k] = [(a, b) for (a, b) in pat[k] if a < n and b < n]
+        for e in pat[k]:
+            angles[e] = (math.pi / 2 + float(rng.uniform(-0.06, 0.06)), math.pi / 6 + float(rng.uniform(-0.06, 0.06)))
+    last = [-1] * n
+    c = []
+    for cycle in range(depth):
+        for q in range(n):
+            k = int(rng.integers(0, 3))
+            if k == last[q]:
+                k = (k + 1 + int(rng.integers(0, 2))) % 3
+            last[q] = k
+            if k == 0:
+                c.append(("Rx", (q,), (math.pi / 2,)))
+            elif k == 1:
+                c.append(("Ry", (q,), (math.pi / 2,)))
+            else:
+                c += [("Rz", (q,), (-math.pi / 4,)), ("Rx", (q,), (math.pi / 2,)), ("Rz", (q,), (math.pi / 4,))]
+        for e in pat["ABCDCDAB"[cycle % 8]]:
+            c.append(("fSim", e, angles[e]))
+    return c
+
+
 # ------------------------------------------------------------------ XASM subset
 _GATE_RE = re.compile(r"^\s*([A-Za-z0-9_]+)\s*\((.*)\)\s*;\s*$")
 

@@ -49,6 +49,7 @@ struct SiteBuf {
 struct QGate {
   int q0, q1;       // q1 < 0: single-qubit gate
   cplx m[16];
+  int skip = 0;     // fuse_2q: the product of the merged gates is the identity, nothing to execute
 };
 
 // bump allocator over one grow-only device buffer
@@ -81,6 +82,13 @@ struct mps_b200_handle {
   double cutoff = DBL_MIN;
   int gauge = 0, device = 0;
   int cutoff_on_sqrt = 0, fuse_1q = 1, renorm = 0, profile = 0, layer_batch = 1, use_qr = 1;
+  // fuse_2q: consecutive 2q gates on the same site pair (and the 1q gates between them) become one 4x4 before they reach
+  // the GPU, e.g. CX.Rz.CX = ZZ(gamma) of the QAOA circuits or Swap.Swap = 1 between two routed gates.
+  // Off by default: the reference truncates after every 2q gate (ExaTnMpsVisitor.cpp:1394-1630), so with truncation
+  // active the fused run is more accurate than, not identical to, the reference; without truncation both are exact.
+  int fuse_2q = 0;
+  std::vector<int> last_touch;   // per site: index in `queue` of the last queued gate on it (-1: none since the flush)
+  double nfused2q = 0;
   double jacobi_tol = 0.0;   // 0 -> sqrt(M) * eps
   double null_tol = 0.0;     // 0 -> 10 * jacobi tolerance
   int max_sweeps = 40;
@@ -112,6 +120,12 @@ struct mps_b200_handle {
   int jacobi_groups = 1;
   int jacobi_persistent = 1;   // one persistent dataflow launch per sweep (jacobi_sweep_kernel) instead of one launch per step
   int sm_count = 148;
+  // persistent sweep kernel: resident CTAs per SM.  0 = by load: the routed circuits (configs 3 and 5) run layers of 2-8
+  // gates, i.e. fewer pair tasks per tournament step than SMs x 4; launching only as many CTAs as there are tasks keeps
+  // such tasks one per SM instead of letting up to four of them share an SM's DMMA / FP64 pipes while other SMs idle
+  int ctas_per_sm = 0;
+  int wide_tasks = 1;      // 8 warps per pair task when at most two tasks per SM are resident (0: always 4)
+  int jacobi_3m_on = 0;    // mirrors jacobi_set_3m (the 3M product exists for 4-warp tasks only)
   int stagger_ns = 0;
   int block16 = 0;   // Jacobi over 16-column blocks (32-column tasks): half the passes through L2 per sweep
   double discard_margin = 0.0;    // discard-aware rotation rule: fraction of the keep-th largest squared column norm (0 = off)
@@ -181,6 +195,7 @@ struct mps_b200_handle {
     CK(cudaStreamSynchronize(stream));
     ++state_ver;
     queue.clear();
+    std::fill(last_touch.begin(), last_touch.end(), -1);
     std::fill(has1q.begin(), has1q.end(), 0);
     measure.clear();
     discarded = 0.0;
@@ -210,6 +225,7 @@ struct mps_b200_handle {
       QGate g;
       g.q0 = q; g.q1 = -1;
       for (int i = 0; i < 4; ++i) g.m[i] = m[i];
+      last_touch[q] = (int)queue.size();
       queue.push_back(g);
       if (!layer_batch) flush();
     }
@@ -239,6 +255,27 @@ struct mps_b200_handle {
         }
       has1q[q0] = has1q[q1] = 0;
     }
+    if (fuse_2q && last_touch[q0] >= 0 && last_touch[q0] == last_touch[q1] && queue[last_touch[q0]].q1 >= 0) {
+      // the last queued gate on both sites is a 2q gate on this very pair: prev <- g * prev (in prev's qubit order)
+      QGate& pv = queue[last_touch[q0]];
+      const bool same = (pv.q0 == q0);
+      cplx t[16];
+      for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+          cplx s = 0;
+          for (int k = 0; k < 4; ++k) {
+            const int rr = same ? r : ((r & 1) << 1 | (r >> 1)), kk = same ? k : ((k & 1) << 1 | (k >> 1));
+            s += g.m[4 * rr + kk] * pv.m[4 * k + c];
+          }
+          t[4 * r + c] = s;
+        }
+      double off = 0;
+      for (int i = 0; i < 16; ++i) { pv.m[i] = t[i]; off = std::max(off, std::abs(t[i] - cplx((i % 5) == 0 ? 1.0 : 0.0, 0.0))); }
+      pv.skip = off < 1e-15;
+      nfused2q += 1;
+      return;
+    }
+    last_touch[q0] = last_touch[q1] = (int)queue.size();
     queue.push_back(g);
     if (!layer_batch) flush();
   }
@@ -251,6 +288,7 @@ struct mps_b200_handle {
       std::vector<std::vector<int>> layers;
       for (size_t i = 0; i < queue.size(); ++i) {
         const QGate& g = queue[i];
+        if (g.skip) continue;
         int l = level[g.q0];
         if (g.q1 >= 0) l = std::max(l, level[g.q1]);
         ++l;
@@ -261,6 +299,7 @@ struct mps_b200_handle {
       }
       for (auto& L : layers) run_layer(L);
       queue.clear();
+      std::fill(last_touch.begin(), last_touch.end(), -1);
     }
     // leftover fused single-qubit gates
     std::vector<Gate1qProblem> p1;
@@ -346,6 +385,7 @@ struct mps_b200_handle {
     for (int b = 0; b < B; ++b) pstride = std::max(pstride, ((D[b].Ng + 7) / 8 + 1) & ~1);
     const size_t oProg = ws.reserve(sizeof(int) * ((size_t)B * pstride + max_sweeps + 4));
     const size_t oThr = ws.reserve(sizeof(double) * B);   // discard-aware thresholds, zero = off (inside the zeroed block)
+    const size_t oActive = ws.reserve(sizeof(int) * (B + 2));   // matrices still rotating: [0] count, [1..] indices (uploaded as "all")
     const size_t oFlags = ws.reserve(sizeof(int) * (2 * B + 4) + sizeof(double) * B + 16);   // dirty[B], done[B], remaining, pad, fro2[B]
     const size_t oKeepBlk = ws.reserve((sizeof(int) + 2 * sizeof(double)) * B + 64);
     size_t sig_total = 0;
@@ -394,6 +434,7 @@ struct mps_b200_handle {
     TruncProblem* hT = (TruncProblem*)(st + (oTr - oGemm));
     QrProblem* hQ = (QrProblem*)(st + (oQr - oGemm));
     int max_tiles = 0, max_pairs = 1, max_steps = 1, maxMg = 1, maxNg = 1;
+    long level_tasks = 0;   // pair tasks per tournament step over the whole layer
     for (int b = 0; b < B; ++b) {
       const QGate& g = queue[g2[b]];
       const Dim& d = D[b];
@@ -431,6 +472,7 @@ struct mps_b200_handle {
         CK(cudaMemsetAsync(wb + d.oVer, 0, sizeof(int) * nbe_ + 8 + sizeof(int2) * nbe_ * nbe_, stream));
       }
       max_pairs = std::max(max_pairs, j.nb == 1 ? 1 : j.nbe / 2);
+      level_tasks += (j.nb == 1 ? 1 : j.nbe / 2);
       max_steps = std::max(max_steps, j.nb == 1 ? 1 : j.nbe - 1);
       maxMg = std::max(maxMg, d.Mg);
       maxNg = std::max(maxNg, d.Ng);
@@ -440,6 +482,11 @@ struct mps_b200_handle {
       t.sig2 = (double*)(wb + d.oSig2); t.sigma = (double*)(wb + d.oSigma); t.perm = (int*)(wb + d.oPerm);
       t.scaleP = (double*)(wb + d.oSP); t.scaleO = (double*)(wb + d.oSO);
       t.keep = (int*)(wb + d.oKeep); t.weights = (double*)(wb + d.oW);
+    }
+    {
+      int* ha = (int*)(st + (oActive - oGemm));
+      ha[0] = B;
+      for (int b = 0; b < B; ++b) ha[1 + b] = b;
     }
     CK(cudaMemcpyAsync(wb + oGemm, st, descBytes, cudaMemcpyHostToDevice, stream));   // flags zeroed too
     int* d_dirty = (int*)(wb + oFlags);
@@ -474,15 +521,28 @@ struct mps_b200_handle {
     if (jacobi_persistent && NG == 1) {
       int* d_prog = (int*)(wb + oProg);
       int* d_cnt = d_prog + (size_t)B * pstride;
+      int* d_active = (int*)(wb + oActive);
       if (trace) CK(cudaEventRecord(ev[5], stream));
+      int rotating = B;
       for (; sweep < max_sweeps; ++sweep) {
+        int per_sm = ctas_per_sm, warps = 4;
+        {
+          // live tasks per tournament step (finished matrices have no slots: d_active); phantom slots of the smaller
+          // matrices of the layer still cost one dequeue each, so a CTA should not walk through more than ~100 per sweep
+          const long est = std::max<long>(1, level_tasks * rotating / B);
+          const long slots = (long)max_steps * rotating * max_pairs;
+          const long want = std::max(est, slots / 96);
+          if (per_sm <= 0) per_sm = (int)std::max<long>(1, std::min<long>(4, (want + sm_count - 1) / sm_count));
+          // at most two tasks per SM: give each task eight warps (the register file holds 2 x 256 threads of this kernel)
+          if (wide_tasks && !jacobi_3m_on && per_sm <= 2) warps = 8;
+        }
         if (block16)
           launch_jacobi_sweep16((const JacobiProblem*)(wb + oJac), B, max_pairs, max_steps, sweep * max_steps, tol2, dead2, d_fro2,
                                 d_dirty, d_done, d_prog, pstride, d_cnt + sweep, d_rem + 1, sm_count, stream);
         else
-        launch_jacobi_sweep((const JacobiProblem*)(wb + oJac), B, max_pairs, max_steps, sweep * max_steps, tol2, dead2, d_fro2, d_dirty,
-                            d_done, d_prog, pstride, d_cnt + sweep, d_rem + 1, sm_count * 4, stagger_ns, stream);
-        launch_jacobi_check(B, d_dirty, d_done, d_rem, stream);
+        launch_jacobi_sweep((const JacobiProblem*)(wb + oJac), rotating, max_pairs, max_steps, sweep * max_steps, tol2, dead2, d_fro2, d_dirty,
+                            d_done, d_prog, pstride, d_cnt + sweep, d_rem + 1, sm_count * per_sm, warps, stagger_ns, d_active, stream);
+        launch_jacobi_check(B, d_dirty, d_done, d_rem, d_active, stream);
         nlaunch += 2;
         if (discard_margin > 0 && maxNg > max_bond) {
           launch_jacobi_thr((const JacobiProblem*)(wb + oJac), B, max_bond, discard_margin, d_done, stream);
@@ -499,6 +559,7 @@ struct mps_b200_handle {
           CK(cudaEventRecord(ev[5], stream));
         }
         if (*h_rem == 0) { ++sweep; break; }
+        rotating = std::min(B, std::max(1, *h_rem));
       }
     } else
     {
@@ -523,7 +584,7 @@ struct mps_b200_handle {
         const int o = goff[g], nb = goff[g + 1] - goff[g];
         for (int st_ = 0; st_ < gsteps[g]; ++st_)
           launch_jacobi_step(dJ + o, nb, gpairs[g], st_, tol2, dead2, d_fro2 + o, d_dirty + o, d_done + o, gs);
-        launch_jacobi_check(nb, d_dirty + o, d_done + o, d_rem + g, gs);
+        launch_jacobi_check(nb, d_dirty + o, d_done + o, d_rem + g, nullptr, gs);
         nlaunch += gsteps[g] + 1;
         const int slot = enq[g] % GDEPTH;
         CK(cudaMemcpyAsync(pin_rem + g * GDEPTH + slot, d_rem + g, sizeof(int), cudaMemcpyDeviceToHost, gs));
@@ -930,6 +991,7 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     h->norm_ver.assign(h->nreg, 0);
     h->norm_val.assign(h->nreg, 0.0);
     h->has1q.assign(h->ntot, 0);
+    h->last_touch.assign(h->ntot, -1);
     h->p1q.resize(h->ntot);
     h->sv.assign(std::max(h->ntot - 1, 1), std::vector<double>{1.0});
     // developer overrides for A/B runs of the whole test-suite
@@ -943,9 +1005,11 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     h->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("MPS_B200_JACOBI_TOL")) h->jacobi_tol = atof(e);
     if (const char* e = getenv("MPS_B200_NULL_TOL")) h->null_tol = atof(e);
-    if (const char* e = getenv("MPS_B200_3M")) jacobi_set_3m(atoi(e));
+    if (const char* e = getenv("MPS_B200_3M")) { jacobi_set_3m(atoi(e)); h->jacobi_3m_on = atoi(e) != 0; }
+    if (const char* e = getenv("MPS_B200_WIDE_TASKS")) h->wide_tasks = atoi(e) != 0;
     if (const char* e = getenv("MPS_B200_QR_LOOKAHEAD")) h->qr_lookahead = atoi(e) != 0;
     if (const char* e = getenv("MPS_B200_BLOCK16")) h->block16 = atoi(e) != 0;
+    if (const char* e = getenv("MPS_B200_CTAS_PER_SM")) h->ctas_per_sm = std::max(0, std::min(4, atoi(e)));
     if (const char* e = getenv("MPS_B200_SMALL_GEMM")) gemm_set_small_path(atoi(e));
     if (seed) h->rng.seed(seed);
     else { std::random_device rd; h->rng.seed(rd()); }   // RandomEngine.hpp:39-42
@@ -992,6 +1056,7 @@ int mps_set_option(mps_handle_t h, const char* key, double value) {
   std::string k(key);
   if (k == "cutoff_on_sqrt") h->cutoff_on_sqrt = value != 0;
   else if (k == "fuse_1q") { h->flush(); h->fuse_1q = value != 0; }
+  else if (k == "fuse_2q") { h->flush(); h->fuse_2q = value != 0; }
   else if (k == "renormalize") h->renorm = value != 0;
   else if (k == "jacobi_tol") h->jacobi_tol = value;
   else if (k == "null_tol") h->null_tol = value;
@@ -1002,9 +1067,11 @@ int mps_set_option(mps_handle_t h, const char* key, double value) {
   else if (k == "jacobi_groups") { h->flush(); h->jacobi_groups = std::max(1, (int)value); }
   else if (k == "jacobi_persistent") { h->flush(); h->jacobi_persistent = value != 0; }
   else if (k == "discard_margin") { h->flush(); h->discard_margin = value; }
-  else if (k == "jacobi_3m") { h->flush(); jacobi_set_3m(value != 0); }
+  else if (k == "jacobi_3m") { h->flush(); jacobi_set_3m(value != 0); h->jacobi_3m_on = value != 0; }
+  else if (k == "jacobi_wide_tasks") { h->flush(); h->wide_tasks = value != 0; }
   else if (k == "qr_lookahead") { h->flush(); h->qr_lookahead = value != 0; }
   else if (k == "jacobi_block16") { h->flush(); h->block16 = value != 0; }
+  else if (k == "jacobi_ctas_per_sm") { h->flush(); h->ctas_per_sm = std::max(0, std::min(4, (int)value)); }
   else if (k == "max_bond") h->max_bond = value > 0 ? (int)value : INT_MAX - 1;
   else if (k == "svd_cutoff") h->cutoff = value >= 0 ? value : DBL_MIN;
   else if (k == "gauge") h->gauge = (int)value;
@@ -1233,8 +1300,8 @@ int mps_stats(mps_handle_t h, double* out, int cap) {
   API_BEGIN(h)
   h->flush();
   CK(cudaStreamSynchronize(h->stream));
-  const double v[10] = {h->n2q, h->n1q, h->nlayers, h->nsweeps, h->nlaunch, h->ms_theta, h->ms_svd, h->ms_wb, h->ms_qr, jacobi_dmma_flops()};
-  for (int i = 0; i < cap && i < 10; ++i) out[i] = v[i];
+  const double v[11] = {h->n2q, h->n1q, h->nlayers, h->nsweeps, h->nlaunch, h->ms_theta, h->ms_svd, h->ms_wb, h->ms_qr, jacobi_dmma_flops(), h->nfused2q};
+  for (int i = 0; i < cap && i < 11; ++i) out[i] = v[i];
   API_END(h)
 }
 

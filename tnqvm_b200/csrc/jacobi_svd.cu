@@ -55,7 +55,9 @@ __device__ __forceinline__ bool pair_blocks(const JacobiProblem& P, int step, in
 // one pair task: Gram (phase A), rotations (phase B), apply (phase C) on the 16 columns of blocks (blkA, blkB).
 // All exits are uniform over the CTA.  Loads of G bypass L1 (ld.global.cg): inside the persistent sweep kernel the
 // columns were last written by a CTA on another SM.
-template <bool M3>
+// NWARP = warps per task: 4 when the SMs hold several tasks each, 8 when a tournament step has fewer tasks than SMs (layers
+// of one to four gates in routed circuits) and the latency of the two streaming phases of a lone task is what counts.
+template <bool M3, int NWARP>
 __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int blkA, int blkB, bool within, double tol2, double dead2,
                                           const double* __restrict__ fro2, int* __restrict__ dirty) {
   const int M = P.M, N = P.N, ldg = P.ldg;
@@ -66,7 +68,8 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   const double thr = *P.thr;   // both columns below thr: both will be truncated, leave the pair alone
 
   __shared__ int s_cols[16];
-  __shared__ double s_red[4][7][64];
+  constexpr int NT = 32 * NWARP;
+  __shared__ double s_red[NWARP][7][64];
   __shared__ double2 sW[16 * WLD];
   __shared__ double2 sQ[16 * WLD];
   __shared__ double s_rc[8];
@@ -123,7 +126,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
       // only the cross block W_AB = X_A^H X_B is computed (4 DMMA per 4 rows instead of 10): the Gram blocks W_AA, W_BB
       // of the two column blocks travel with them (P.wd), kept up to date by the two-sided rotations of every task and
       // recomputed from the columns at the first step of each tournament
-      for (int base = warp * UN; base < nch; base += 4 * UN) {
+      for (int base = warp * UN; base < nch; base += NWARP * UN) {
         double2 x0[UN], x1[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
@@ -141,7 +144,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
         }
       }
     } else
-    for (int base = warp * UN; base < nch; base += 4 * UN) {
+    for (int base = warp * UN; base < nch; base += NWARP * UN) {
       double2 x0[UN], x1[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
@@ -176,14 +179,17 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   }
   __syncthreads();
   if (timing) tB = clock64();
-  for (int i = tid + (within ? 0 : 4 * 64); i < 7 * 64; i += JT) {
+  for (int i = tid + (within ? 0 : 4 * 64); i < 7 * 64; i += NT) {
     const int t = i >> 6, e = i & 63;
-    s_red[0][t][e] = s_red[0][t][e] + s_red[1][t][e] + s_red[2][t][e] + s_red[3][t][e];
+    double acc = s_red[0][t][e];
+#pragma unroll
+    for (int w = 1; w < NWARP; ++w) acc += s_red[w][t][e];
+    s_red[0][t][e] = acc;
   }
   __syncthreads();
   const double2* wdA = P.wd + (size_t)blkA * 64;
   const double2* wdB = P.wd + (size_t)(blkB >= 0 ? blkB : blkA) * 64;
-  for (int i = tid; i < 256; i += JT) {
+  for (int i = tid; i < 256; i += NT) {
     const int p = i >> 4, q = i & 15;
     const int bp = p >> 3, bq = q >> 3, r = p & 7, c = q & 7;
     double re, im;
@@ -199,7 +205,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   // fresh-Gram convergence test over the pairs this task is responsible for
   {
     int need = 0;
-    for (int i = tid; i < 256; i += JT) {
+    for (int i = tid; i < 256; i += NT) {
       const int p = i >> 4, q = i & 15;
       if (p < q && (within || (p < 8 && q >= 8))) {   // pairs inside a block belong to the first step of the tournament
         const double a = sW[p * WLD + p].x, b = sW[q * WLD + q].x;
@@ -217,7 +223,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
       const int va = blkA < blkB ? verA : verB, vb = blkA < blkB ? verB : verA;
       *recp = make_int2(va + 1, vb + 1);
     }
-    if (within) {   // the tournament's first step refreshes the travelling Gram blocks from the columns
+    if (within && tid < 128) {   // the tournament's first step refreshes the travelling Gram blocks from the columns
       const int bb = tid >> 6, r = (tid >> 3) & 7, c = tid & 7;
       if (bb == 0 || blkB >= 0) P.wd[(size_t)(bb ? blkB : blkA) * 64 + r * 8 + c] = sW[(8 * bb + r) * WLD + 8 * bb + c];
     }
@@ -280,7 +286,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
         sW[pa * WLD + qb] = cadd(cmul(sb, t00), rmul(cb, t01));
         sW[qa * WLD + pb] = csub(rmul(cb, t10), cmulc(sb, t11));
         sW[qa * WLD + qb] = cadd(cmul(sb, t10), rmul(cb, t11));
-      } else {
+      } else if (warp < 4) {
         // Q <- Q J
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -303,7 +309,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     P.ver[blkA] = verA + 1;
     if (blkB >= 0) P.ver[blkB] = verB + 1;
   }
-  {
+  if (tid < 128) {
     const int bb = tid >> 6, r = (tid >> 3) & 7, c = tid & 7;
     if (bb == 0 || blkB >= 0) P.wd[(size_t)(bb ? blkB : blkA) * 64 + r * 8 + c] = sW[(8 * bb + r) * WLD + 8 * bb + c];
   }
@@ -338,7 +344,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
       }
     const int nch = (M + 7) >> 3;
     constexpr int UN = 2;
-    for (int base = warp * UN; base < nch; base += 4 * UN) {
+    for (int base = warp * UN; base < nch; base += NWARP * UN) {
       double2 xa[UN][4];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem*
   int blkA, blkB;
   bool within;
   if (!pair_blocks(P, step, blockIdx.x, blkA, blkB, within)) return;
-  pair_task<M3>(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
+  pair_task<M3, 4>(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
 }
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -427,13 +433,15 @@ __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.rel
 // Tasks are dequeued in dependency order and a waiting CTA only waits on tasks dequeued before its own, which are
 // finished or running on resident CTAs, so the scheme cannot deadlock.  Compared with one launch per step this removes
 // ~60 launch boundaries per sweep and lets the Gram / rotate / apply phases of different pairs overlap on an SM.
-template <bool M3>
-__global__ void __launch_bounds__(JT, 4) jacobi_sweep_kernel(const JacobiProblem* __restrict__ probs, int batch, int max_pairs, int nsteps,
+template <bool M3, int NWARP>
+__global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) jacobi_sweep_kernel(const JacobiProblem* __restrict__ probs, int batch, int max_pairs, int nsteps,
                                                              int base, double tol2, double dead2, const double* __restrict__ fro2,
                                                              int* __restrict__ dirty, const int* __restrict__ done,
                                                              int* __restrict__ progress, int progress_stride, int* __restrict__ counter,
-                                                             int* __restrict__ fault, int stagger_ns) {
+                                                             int* __restrict__ fault, int stagger_ns, const int* __restrict__ active) {
   __shared__ int s_task;
+  // active (optional): [0] = number of matrices still rotating, [1..] their indices (written by jacobi_check_kernel)
+  if (active) batch = __ldcg(active);
   const int per_step = batch * max_pairs;
   const int total = nsteps * per_step;
   for (;;) {
@@ -443,7 +451,8 @@ __global__ void __launch_bounds__(JT, 4) jacobi_sweep_kernel(const JacobiProblem
     __syncthreads();   // s_task may be overwritten from here on
     if (t >= total) return;
     const int step = t / per_step, r = t - step * per_step;
-    const int mat = r / max_pairs, pi = r - mat * max_pairs;
+    const int slot = r / max_pairs, pi = r - slot * max_pairs;
+    const int mat = active ? __ldcg(active + 1 + slot) : slot;
     if (done[mat]) continue;
     const JacobiProblem P = probs[mat];
     const int npairs = (P.nb == 1) ? 1 : P.nbe / 2;
@@ -471,7 +480,7 @@ __global__ void __launch_bounds__(JT, 4) jacobi_sweep_kernel(const JacobiProblem
     }
     __syncthreads();
     if (threadIdx.x == 0 && g_dbg_mode == 10) atomicAdd(&g_phase_cycles[4], (unsigned long long)(clock64() - tw));
-    pair_task<M3>(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
+    pair_task<M3, NWARP>(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -923,19 +932,39 @@ __global__ void __launch_bounds__(256) jacobi_thr_kernel(const JacobiProblem* __
   }
 }
 
-__global__ void jacobi_check_kernel(int batch, int* dirty, int* done, int* remaining) {
-  __shared__ int cnt;
-  if (threadIdx.x == 0) cnt = 0;
-  __syncthreads();
-  for (int m = threadIdx.x; m < batch; m += blockDim.x) {
+// After a sweep: a matrix that went through it without a rotation is done.  Also compacts the matrices still rotating into
+// active[1..] (active[0] = their number) so that the next sweep's task space holds no slots of finished matrices: the last
+// sweeps of a layer are run by one or two stragglers, and walking through the dead slots of the other matrices used to cost
+// every CTA one global atomic per slot.
+__global__ void __launch_bounds__(256) jacobi_check_kernel(int batch, int* dirty, int* done, int* remaining, int* active) {
+  __shared__ int s_cnt[256];
+  __shared__ int s_off[257];
+  const int tid = threadIdx.x;
+  const int per = (batch + 255) / 256;
+  const int lo = min(batch, tid * per), hi = min(batch, lo + per);
+  int c = 0;
+  for (int m = lo; m < hi; ++m) {
     if (!done[m]) {
       if (!dirty[m]) done[m] = 1;
-      else atomicAdd(&cnt, 1);
+      else ++c;
     }
     dirty[m] = 0;
   }
+  s_cnt[tid] = c;
   __syncthreads();
-  if (threadIdx.x == 0) *remaining = cnt;
+  if (tid == 0) {
+    int o = 0;
+    for (int i = 0; i < 256; ++i) { s_off[i] = o; o += s_cnt[i]; }
+    s_off[256] = o;
+    *remaining = o;
+    if (active) active[0] = o;
+  }
+  __syncthreads();
+  if (active) {
+    int o = s_off[tid];
+    for (int m = lo; m < hi; ++m)
+      if (!done[m]) active[1 + o++] = m;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1032,16 +1061,19 @@ void launch_jacobi_step(const JacobiProblem* d_probs, int batch, int max_pairs, 
 }
 void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
                          const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
-                         int* d_fault, int grid_ctas, int stagger_ns, cudaStream_t s) {
+                         int* d_fault, int grid_ctas, int warps_per_task, int stagger_ns, const int* d_active, cudaStream_t s) {
   if (batch <= 0) return;
-  const long total = (long)nsteps * batch * max_pairs;
+  const long total = (long)nsteps * batch * max_pairs;   // batch = matrices still rotating when d_active is given
   const int grid = (int)std::min<long>(total, grid_ctas);
-  if (g_use_3m)
-    jacobi_sweep_kernel<true><<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done, d_progress,
-                                                  progress_stride, d_counter, d_fault, stagger_ns);
+  if (warps_per_task == 8)
+    jacobi_sweep_kernel<false, 8><<<grid, 256, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
+                                                      d_progress, progress_stride, d_counter, d_fault, stagger_ns, d_active);
+  else if (g_use_3m)
+    jacobi_sweep_kernel<true, 4><<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
+                                                     d_progress, progress_stride, d_counter, d_fault, stagger_ns, d_active);
   else
-    jacobi_sweep_kernel<false><<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
-                                                   d_progress, progress_stride, d_counter, d_fault, stagger_ns);
+    jacobi_sweep_kernel<false, 4><<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
+                                                      d_progress, progress_stride, d_counter, d_fault, stagger_ns, d_active);
 }
 void launch_jacobi_sweep16(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
                            const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
@@ -1079,8 +1111,8 @@ void launch_fro2(const JacobiProblem* d_probs, int batch, double* d_fro2, cudaSt
   dim3 grid(16, batch);
   fro2_kernel<<<grid, 256, 0, s>>>(d_probs, d_fro2);
 }
-void launch_jacobi_check(int batch, int* d_dirty, int* d_done, int* d_remaining, cudaStream_t s) {
-  jacobi_check_kernel<<<1, 256, 0, s>>>(batch, d_dirty, d_done, d_remaining);
+void launch_jacobi_check(int batch, int* d_dirty, int* d_done, int* d_remaining, int* d_active, cudaStream_t s) {
+  jacobi_check_kernel<<<1, 256, 0, s>>>(batch, d_dirty, d_done, d_remaining, d_active);
 }
 void launch_trunc(const TruncProblem* d_probs, int batch, double cutoff, int cutoff_on_sqrt, int max_bond, int gauge, int renorm,
                   double null_tol, cudaStream_t s) {

@@ -75,7 +75,8 @@ void launch_jacobi_step(const JacobiProblem* d_probs, int batch, int max_pairs, 
 // per SVD; base = steps completed by the previous sweeps; *d_counter zeroed (one counter per launch)
 void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
                          const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
-                         int* d_fault, int grid_ctas, int stagger_ns, cudaStream_t s);   // *d_fault += 1 if a dependency wait timed out
+                         int* d_fault, int grid_ctas, int warps_per_task /* 4 or 8 */, int stagger_ns,
+                         const int* d_active /* optional: [0] = matrices still rotating (= batch), [1..] their indices */, cudaStream_t s);   // *d_fault += 1 if a dependency wait timed out
 // the same sweep over 16-column blocks (JacobiProblem.nb / nbe count 16-column blocks, wd holds 256 complex per block)
 void launch_jacobi_sweep16(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
                            const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
@@ -86,7 +87,7 @@ void jacobi_set_3m(int on);   // 3M complex product in the column update (defaul
 double jacobi_dmma_flops();   // process-wide count of real flops the Jacobi pair tasks issued on the DMMA pipe
 void launch_fro2(const JacobiProblem* d_probs, int batch, double* d_fro2, cudaStream_t s);   // d_fro2 pre-zeroed
 // after a sweep: done[m] |= !dirty[m]; dirty[m] = 0; *remaining = #not done
-void launch_jacobi_check(int batch, int* d_dirty, int* d_done, int* d_remaining, cudaStream_t s);
+void launch_jacobi_check(int batch, int* d_dirty, int* d_done, int* d_remaining, int* d_active /* may be null */, cudaStream_t s);
 
 // column norms, descending sort, truncation rule (ExaTnMpsVisitor.cpp:2434-2445) and write-back scales
 struct TruncProblem {

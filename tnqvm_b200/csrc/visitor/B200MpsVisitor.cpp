@@ -95,6 +95,9 @@ void B200MpsVisitor::initialize(std::shared_ptr<AcceleratorBuffer> in_buffer, in
   }
   if (options.keyExists<bool>("b200-cutoff-on-sqrt") && options.get<bool>("b200-cutoff-on-sqrt"))
     check(mps_set_option(m_handle, "cutoff_on_sqrt", 1.0), "set_option");
+  // not a reference option: merge consecutive 2q gates on one site pair into one 4x4 (CX.Rz.CX, Swap.Swap) before the GPU
+  if (options.keyExists<bool>("b200-fuse-2q") && options.get<bool>("b200-fuse-2q"))
+    check(mps_set_option(m_handle, "fuse_2q", 1.0), "set_option");
 }
 
 void B200MpsVisitor::applyGate(xacc::Instruction& inst) {
