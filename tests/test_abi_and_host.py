@@ -88,3 +88,21 @@ def test_config_generators_shapes():
         n, c = Cc.load_xasm(open(syc).read())
         assert n == 53 and Cc.count_gates(c) == (2527, 301)
         assert Cc.count_gates(Cc.nearest_neighbor(c))[1] == 1897
+
+
+def test_sycamore_grid_stand_in_has_the_shape_of_the_resource_file():
+    """C5 on the GPU box (no /root/reference there): 53 qubits, 14 cycles, ~20-27 fSim per cycle in the ABCDCDAB pattern
+    order, per-coupler angles near (pi/2, pi/6), long-range couplers that the nearest-neighbour pass routes."""
+    import math
+    c = Cc.sycamore_grid()
+    assert max(max(g[1]) for g in c) == 52
+    fs = [g for g in c if g[0] == "fSim"]
+    assert len(fs) == 320 and {abs(g[1][0] - g[1][1]) for g in fs} == {1, 6}
+    assert all(abs(g[2][0] - math.pi / 2) < 0.07 and abs(g[2][1] - math.pi / 6) < 0.07 for g in fs)
+    ang = {}
+    for g in fs:
+        assert ang.setdefault(g[1], g[2]) == g[2]          # one angle pair per coupler, every time it fires
+    nn = Cc.nearest_neighbor(c)
+    assert Cc.count_gates(nn) == (1240, 2200)
+    assert all(abs(g[1][0] - g[1][1]) == 1 for g in nn if len(g[1]) == 2)
+    assert Cc.sycamore_grid(seed=0) == c and Cc.sycamore_grid(seed=1) != c
