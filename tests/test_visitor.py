@@ -92,3 +92,28 @@ def test_visitor_large_register_sampling_and_norm():
     # amplitude output (computeWaveFuncSlice with a closed bit string, ExaTnMpsVisitor.cpp:2588-2675): GHZ 1/sqrt(2)
     res = json.loads(run([g for g in RC.ghz4_measured() if g[0] != "Measure"], 4, "--bitstring", "1111"))
     assert abs(res["amplitude"][0] - math.sqrt(0.5)) < 1e-12 and abs(res["amplitude"][1]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_visitor_bitstring_option_amplitude_and_slice():
+    """{"bitstring", vector<int>} as in ExaTnMpsVisitor.cpp:776-822: every leg fixed -> "amplitude-real"/"amplitude-imag";
+    legs marked -1 -> the normalised slice in "amplitude-real-vec"/"amplitude-imag-vec" (ExatnVisitorTester.cpp:533-651 asserts
+    the same GHZ values on the exatn visitor).  Also the b200-fuse-2q switch through the visitor options."""
+    ghz = [g for g in RC.ghz4_measured() if g[0] != "Measure"]
+    res = json.loads(run(ghz, 4, "--bitstring", "0000"))
+    assert abs(res["amplitude"][0] - math.sqrt(0.5)) < 1e-12 and "amplitude_slice" not in res
+    res = json.loads(run(ghz, 4, "--bitstring", "0110"))
+    assert abs(res["amplitude"][0]) < 1e-12 and abs(res["amplitude"][1]) < 1e-12
+    # q0 = q3 = 1 fixed, q1 and q2 open: only |11> of the open pair survives, normalised to 1 (open qubit q1 fastest)
+    res = json.loads(run(ghz, 4, "--bitstring", "1xx1"))
+    sl = np.array([complex(a, b) for a, b in res["amplitude_slice"]])
+    assert sl.shape == (4,) and abs(abs(sl[3]) - 1.0) < 1e-12 and np.abs(sl[:3]).max() < 1e-12
+    # all legs open on a product-free circuit: the slice is the normalised state vector
+    circ = Cc.brickwork(5, 4, seed=2)
+    res = json.loads(run(circ, 5, "--bitstring", "xxxxx", "--state", "--fuse-2q"))
+    sl = np.array([complex(a, b) for a, b in res["amplitude_slice"]])
+    sv = np.array([complex(a, b) for a, b in res["state"]])
+    assert np.abs(sl - sv / np.linalg.norm(sv)).max() < 1e-12
+    # wrong length -> the reference's error
+    p = subprocess.run([RUN, "--xasm", "-", "--qubits", "4", "--bitstring", "01"], input=Cc.to_xasm(ghz), capture_output=True, text=True)
+    assert p.returncode != 0 and "Bitstring size must match" in p.stderr

@@ -146,6 +146,32 @@ void B200MpsVisitor::finalize() {
       for (int s = 0; s < produced; ++s) m_buffer->appendMeasurement(std::string(out.data() + (size_t)s * nm, nm));
     }
   }
+  // {"bitstring", vector<int>}: amplitude of one bit string, or the normalised wave-function slice over the legs marked -1
+  // (ExaTnMpsVisitor.cpp:776-822; the reference offers it in its MPI build only, same buffer keys here)
+  if (options.keyExists<std::vector<int>>("bitstring")) {
+    const std::vector<int> bitString = options.get<std::vector<int>>("bitstring");
+    if ((int)bitString.size() != m_nQubits) xacc::error("Bitstring size must match the number of qubits.");
+    int nOpen = 0;
+    for (int v : bitString) nOpen += (v < 0);
+    if (nOpen > 24) xacc::error("bitstring: more than 24 open legs");
+    std::vector<int8_t> b(bitString.begin(), bitString.end());
+    std::vector<std::complex<double>> slice((size_t)1 << nOpen);
+    size_t len = 0;
+    check(mps_amplitude(m_handle, 0, b.data(), reinterpret_cast<double*>(slice.data()), &len), "amplitude");
+    if (slice.size() == 1) {
+      m_buffer->addExtraInfo("amplitude-real", slice[0].real());
+      m_buffer->addExtraInfo("amplitude-imag", slice[0].imag());
+    } else {
+      double nv = 0.0;
+      for (const auto& v : slice) nv += std::norm(v);
+      const double scale = nv > 1e-12 ? 1.0 / std::sqrt(nv) : 1.0;   // a slice of zero norm stays as it is (:794-806)
+      std::vector<double> re, im;
+      re.reserve(slice.size()); im.reserve(slice.size());
+      for (const auto& v : slice) { re.push_back(v.real() * scale); im.push_back(v.imag() * scale); }
+      m_buffer->addExtraInfo("amplitude-real-vec", re);
+      m_buffer->addExtraInfo("amplitude-imag-vec", im);
+    }
+  }
   std::vector<double> st = engineStats();
   executionInfo.insert("b200-gates-2q", st[0]);
   executionInfo.insert("b200-kernel-launches", st[4]);

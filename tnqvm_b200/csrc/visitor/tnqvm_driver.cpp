@@ -141,7 +141,7 @@ int main(int argc, char** argv) {
   std::string file;
   int nq = 0, shots = -1, maxBond = 0, seed = -1, device = 0, gauge = 0;
   double cutoff = -1.0;
-  bool wantState = false, dumpNN = false;
+  bool wantState = false, dumpNN = false, fuse2q = false;
   std::string bitstring;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
@@ -157,7 +157,8 @@ int main(int argc, char** argv) {
     else if (a == "--state") wantState = true;
     else if (a == "--dump-nn") dumpNN = true;   // print the nearest-neighbourised program and exit (no GPU needed)
     else if (a == "--bitstring") bitstring = next();
-    else { fprintf(stderr, "usage: b200_tnqvm_run --xasm FILE|- [--qubits N] [--shots S] [--max-bond-dim D] [--svd-cutoff E] [--seed K] [--state] [--bitstring 0101..]\n"); return 2; }
+    else if (a == "--fuse-2q") fuse2q = true;
+    else { fprintf(stderr, "usage: b200_tnqvm_run --xasm FILE|- [--qubits N] [--shots S] [--max-bond-dim D] [--svd-cutoff E] [--seed K] [--state] [--bitstring 01x1..] [--fuse-2q]\n"); return 2; }
   }
   try {
     std::stringstream ss;
@@ -182,6 +183,12 @@ int main(int argc, char** argv) {
     if (maxBond > 0) opts.insert("max-bond-dim", maxBond);
     if (cutoff >= 0) opts.insert("svd-cutoff", cutoff);
     if (seed >= 0) opts.insert("seed", seed);
+    if (!bitstring.empty()) {   // '0'/'1' fix a leg, any other character ('x', '-') leaves it open
+      std::vector<int> bits;
+      for (char c : bitstring) bits.push_back(c == '0' ? 0 : c == '1' ? 1 : -1);
+      opts.insert("bitstring", bits);
+    }
+    if (fuse2q) opts.insert("b200-fuse-2q", true);
     opts.insert("b200-device", device);
     opts.insert("b200-gauge", gauge);
     auto visitor = std::make_shared<tnqvm::B200MpsVisitor>();
@@ -199,11 +206,14 @@ int main(int argc, char** argv) {
     auto bd = visitor->bondDimensions();
     for (size_t i = 0; i < bd.size(); ++i) printf("%s%d", i ? ", " : "", bd[i]);
     printf("], \"discarded_weight\": %.17g", visitor->discardedWeight());
-    if (!bitstring.empty()) {
-      std::vector<int> bits;
-      for (char c : bitstring) bits.push_back(c == '1');
-      const auto amp = visitor->amplitude(bits);
-      printf(", \"amplitude\": [%.17g, %.17g]", amp.real(), amp.imag());
+    if (buffer->hasExtraInfoKey("amplitude-real"))   // {"bitstring", ...} with every leg fixed
+      printf(", \"amplitude\": [%.17g, %.17g]", std::get<double>((*buffer)["amplitude-real"]), std::get<double>((*buffer)["amplitude-imag"]));
+    if (buffer->hasExtraInfoKey("amplitude-real-vec")) {
+      const auto& re = std::get<std::vector<double>>((*buffer)["amplitude-real-vec"]);
+      const auto& im = std::get<std::vector<double>>((*buffer)["amplitude-imag-vec"]);
+      printf(", \"amplitude_slice\": [");
+      for (size_t i = 0; i < re.size(); ++i) printf("%s[%.17g, %.17g]", i ? ", " : "", re[i], im[i]);
+      printf("]");
     }
     if (wantState) {
       auto sv = visitor->getState();
