@@ -43,6 +43,11 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
 int mps_destroy(mps_handle_t h);
 const char* mps_last_error(mps_handle_t h); /* h may be NULL: last mps_create error */
 int mps_reset(mps_handle_t h);              /* back to |0...0>, ExaTnMpsVisitor.cpp:273-326 */
+/* VQE mode (TNQVM.cpp:52-92, TNQVMVisitor::supportVqeMode): the ansatz is applied once, then every observable term runs its
+ * change-of-basis gates on that state.  mps_snapshot remembers the current state of all registers on the device (sites, bond
+ * spectra, discarded weight); mps_restore goes back to it.  The measure list is not part of the state (mps_clear_measure). */
+int mps_snapshot(mps_handle_t h);
+int mps_restore(mps_handle_t h);
 
 /* keys: "max_bond", "svd_cutoff", "gauge" (as in mps_create), "cutoff_on_sqrt" (computePartialNormsSync ambiguity,
  * SURVEY 8c), "fuse_1q", "fuse_2q" (default 0: merge consecutive 2q gates on one site pair into one 4x4 -- fewer SVDs, but with

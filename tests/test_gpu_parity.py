@@ -405,3 +405,30 @@ def test_fuse_2q_merges_same_pair_gates_and_stays_exact(O):
     fb = abs(np.vdot(ref, sb)) ** 2 / np.vdot(sb, sb).real
     assert fa > 0.9 and fb >= fa - 5e-3
     a.close(); b.close()
+
+
+def test_snapshot_restore_returns_the_exact_state(O):
+    """mps_snapshot / mps_restore (VQE mode, TNQVM.cpp:52-92): after a restore the sites, bond dimensions, bond spectra and
+    the discarded weight are bit-for-bit those of the snapshot, whatever ran in between (here: gates that grow and truncate
+    the bonds), and the observables of the restored state equal the oracle's for the circuit up to the snapshot."""
+    n, chi = 10, 8
+    circ = Cc.brickwork(n, 6, seed=17)
+    e = tnqvm_b200.B200MPS(n, max_bond=chi)
+    with pytest.raises(tnqvm_b200.abi.MpsError):
+        e.restore()
+    e.run(circ)
+    e.snapshot()
+    sites0 = [e.get_site(k).copy() for k in range(n)]
+    bonds0, sv0, dw0 = e.bond_dims().copy(), e.singular_values(n // 2).copy(), e.discarded_weight()
+    for rep in range(2):
+        e.run(Cc.brickwork(n, 4, seed=40 + rep) + [("Swap", (2, 3), ()), ("fSim", (5, 4), (0.3, 0.7))])
+        assert e.discarded_weight() > dw0
+        assert np.abs(e.get_site(n // 2) - sites0[n // 2]).max() > 1e-3 if e.get_site(n // 2).shape == sites0[n // 2].shape else True
+        e.restore()
+        assert (e.bond_dims() == bonds0).all() and e.discarded_weight() == dw0
+        assert np.array_equal(e.singular_values(n // 2), sv0)
+        for k in range(n):
+            assert np.array_equal(e.get_site(k), sites0[k])
+    o = O.OracleMPS(n, max_bond=chi).run(circ)
+    assert np.abs(e.expval_z_all() - np.array([o.expval_z([k]) for k in range(n)])).max() < TRUNC_TOL
+    e.close()

@@ -117,3 +117,31 @@ def test_visitor_bitstring_option_amplitude_and_slice():
     # wrong length -> the reference's error
     p = subprocess.run([RUN, "--xasm", "-", "--qubits", "4", "--bitstring", "01"], input=Cc.to_xasm(ghz), capture_output=True, text=True)
     assert p.returncode != 0 and "Bitstring size must match" in p.stderr
+
+
+@pytest.mark.gpu
+def test_visitor_vqe_mode_one_ansatz_many_terms():
+    """TNQVM.cpp:52-92 with supportVqeMode(): the ansatz runs once, every observable term goes through
+    getExpectationValueZ (change of basis + Measure) and must leave the ansatz state behind it
+    (ITensorMPSVisitor.cpp:440-464 is the reference's implementation of that contract).  Each term must equal the
+    "exp-val-z" of a full separate run of ansatz + term (VQEModeTester.cpp compares the two modes the same way)."""
+    n = 6
+    ansatz = Cc.hea(n, 2, seed=5) + [("CNOT", (0, 3), ()), ("Ry", (2,), (0.7,))]    # one long-range gate: routed by the pass
+    terms = ["Z0", "X0X1", "Y2Y3", "Z1Z4", "X0Y2Z5", "Z0"]
+    res = json.loads(run(ansatz, n, "--observe", ";".join(terms), "--state"))
+    assert len(res["vqe_terms"]) == len(terms)
+    assert abs(res["vqe_terms"][0] - res["vqe_terms"][-1]) < 1e-13                # the ansatz state came back
+    basis = {"X": lambda q: [("H", (q,), ())], "Y": lambda q: [("Rx", (q,), (math.pi / 2,))], "Z": lambda q: []}
+    import re
+    for t, val in zip(terms, res["vqe_terms"]):
+        ops = [(m.group(1), int(m.group(2))) for m in re.finditer(r"([XYZ])(\d+)", t)]
+        circ = list(ansatz)
+        for p, q in ops:
+            circ += basis[p](q)
+        circ += [("Measure", (q,), ()) for _, q in ops]
+        one = json.loads(run(circ, n))
+        assert abs(one["exp-val-z"] - val) < 1e-10, t
+    base = json.loads(run(ansatz, n, "--state"))
+    sv = np.array([complex(a, b) for a, b in res["state"]])
+    sv0 = np.array([complex(a, b) for a, b in base["state"]])
+    assert np.abs(sv - sv0).max() < 1e-12

@@ -32,6 +32,8 @@ SYMBOLS = {
     "mps_expval_zz_pairs": ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "mps_amplitude": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)], C.c_int),
     "mps_statevector": ([C.c_void_p, C.c_int, C.c_void_p], C.c_int),
+    "mps_snapshot": ([C.c_void_p], C.c_int),
+    "mps_restore": ([C.c_void_p], C.c_int),
     "mps_measure": ([C.c_void_p, C.c_int], C.c_int),
     "mps_clear_measure": ([C.c_void_p], C.c_int),
     "mps_seed": ([C.c_void_p, C.c_uint64], C.c_int),

@@ -94,6 +94,11 @@ struct mps_b200_handle {
   int max_sweeps = 40;
   cudaStream_t stream = nullptr;
   std::vector<SiteBuf> sites;
+  // VQE mode: the ansatz state every observable term starts from (mps_snapshot / mps_restore)
+  std::vector<SiteBuf> snap;
+  std::vector<std::vector<double>> snap_sv;
+  double snap_discarded = 0.0;
+  bool has_snap = false;
   std::vector<char> has1q;
   std::vector<std::array<cplx, 4>> p1q;
   std::vector<QGate> queue;
@@ -206,6 +211,39 @@ struct mps_b200_handle {
     }
     CK(cudaStreamSynchronize(stream));
     for (auto& v : sv) v.assign(1, 1.0);
+  }
+
+  // remember / go back to the current state of all registers (device-to-device, stream-ordered; no host copy)
+  void snapshot_state() {
+    flush();
+    snap.resize(ntot);
+    for (int k = 0; k < ntot; ++k) {
+      const SiteBuf& s = sites[k];
+      SiteBuf& c = snap[k];
+      const size_t need = (size_t)2 * s.dl * s.dr;
+      if (need > c.cap) {
+        if (c.d) CK(cudaFreeAsync(c.d, stream));
+        CK(cudaMallocAsync((void**)&c.d, need * sizeof(double2), stream));
+        c.cap = need;
+      }
+      c.dl = s.dl; c.dr = s.dr;
+      CK(cudaMemcpyAsync(c.d, s.d, need * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+    }
+    snap_sv = sv;
+    snap_discarded = discarded;
+    has_snap = true;
+  }
+  void restore_state() {
+    if (!has_snap) throw std::runtime_error("mps_restore without mps_snapshot");
+    flush();
+    ++state_ver;
+    for (int k = 0; k < ntot; ++k) {
+      const SiteBuf& c = snap[k];
+      ensure_site(k, c.dl, c.dr, false);
+      CK(cudaMemcpyAsync(sites[k].d, c.d, (size_t)2 * c.dl * c.dr * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+    }
+    sv = snap_sv;
+    discarded = snap_discarded;
   }
 
   int reg_of(int q) const { return q / nq; }
@@ -1029,6 +1067,7 @@ int mps_destroy(mps_handle_t h) {
   cudaStreamSynchronize(h->stream);
   if (getenv("MPS_B200_DBG_MODE")) jacobi_print_phase_timing();
   for (auto& s : h->sites) if (s.d) cudaFreeAsync(s.d, h->stream);
+  for (auto& s : h->snap) if (s.d) cudaFreeAsync(s.d, h->stream);
   cudaStreamSynchronize(h->stream);
   if (h->ws.base) cudaFree(h->ws.base);
   for (int i = 0; i < 2; ++i) if (h->pin[i]) cudaFreeHost(h->pin[i]);
@@ -1050,6 +1089,8 @@ int mps_destroy(mps_handle_t h) {
 const char* mps_last_error(mps_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int mps_reset(mps_handle_t h) { API_BEGIN(h) h->reset_state(); API_END(h) }
+int mps_snapshot(mps_handle_t h) { API_BEGIN(h) h->snapshot_state(); API_END(h) }
+int mps_restore(mps_handle_t h) { API_BEGIN(h) h->restore_state(); API_END(h) }
 
 int mps_set_option(mps_handle_t h, const char* key, double value) {
   API_BEGIN(h)

@@ -179,19 +179,30 @@ void B200MpsVisitor::finalize() {
 }
 
 const double B200MpsVisitor::getExpectationValueZ(std::shared_ptr<CompositeInstruction> function) {
-  // ExaTnMpsVisitor.cpp:1087-1117 walks the circuit and then estimates <Z...Z> from 100000 samples; here the same
-  // quantity is computed exactly by one transfer-matrix sweep.
+  // VQE mode (TNQVM.cpp:52-92): the ansatz has been applied once; every observable term arrives here as its change-of-basis
+  // gates plus Measure instructions.  Like the reference's VQE-capable MPS visitor (ITensorMPSVisitor.cpp:440-464) the ansatz
+  // state is cached, the term applied, <Z...Z> taken over the measured qubits, and the ansatz state put back -- here on the
+  // device (mps_snapshot / mps_restore), and the expectation by one transfer-matrix sweep instead of the 100000-shot estimate
+  // of ExaTnMpsVisitor.cpp:1087-1117.
+  if (!m_handle) xacc::error("B200MpsVisitor::getExpectationValueZ called before initialize");
+  check(mps_snapshot(m_handle), "snapshot");
+  std::vector<int> q;
   InstructionIterator it(function);
   while (it.hasNext()) {
     auto inst = it.next();
-    if (inst->isEnabled()) inst->accept(this);
+    if (!inst->isEnabled()) continue;
+    if (inst->name() == "Measure") q.push_back((int)inst->bits()[0]);
+    else inst->accept(this);
   }
-  if (m_measureQubits.empty()) return 0.0;
-  std::vector<int> q(m_measureQubits.begin(), m_measureQubits.end());
-  double ez = 0.0, nrm = 1.0;
-  check(mps_expval_z(m_handle, 0, (int)q.size(), q.data(), &ez), "expval_z");
-  check(mps_norm(m_handle, 0, &nrm), "norm");
-  return nrm > 0 ? ez / nrm : 0.0;   // the sampled estimate of the reference is implicitly normalised
+  double result = 0.0;
+  if (!q.empty()) {
+    double ez = 0.0, nrm = 1.0;
+    check(mps_expval_z(m_handle, 0, (int)q.size(), q.data(), &ez), "expval_z");
+    check(mps_norm(m_handle, 0, &nrm), "norm");
+    result = nrm > 0 ? ez / nrm : 0.0;   // the sampled estimate of the reference is implicitly normalised
+  }
+  check(mps_restore(m_handle), "restore");
+  return result;
 }
 
 const std::vector<std::complex<double>> B200MpsVisitor::getState() {

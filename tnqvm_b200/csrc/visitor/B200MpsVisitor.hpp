@@ -58,6 +58,8 @@ public:
 #endif
 
   const double getExpectationValueZ(std::shared_ptr<CompositeInstruction> function) override;
+  // one ansatz MPS serves all observable terms (TNQVM.cpp:52-92); the reference exatn-mps visitor leaves this false
+  bool supportVqeMode() const override { return true; }
   const std::vector<std::complex<double>> getState() override;
 
   // not part of the reference surface: engine counters for getExecutionInfo()-style reporting

@@ -135,6 +135,43 @@ void execute(std::shared_ptr<tnqvm::TNQVMVisitor> visitor, const HeterogeneousMa
   }
   visitor->finalize();
 }
+
+// TNQVM::execute(buffer, vector<kernels>) in VQE mode, tnqvm/TNQVM.cpp:52-92: the base (ansatz) kernel once, then one
+// getExpectationValueZ per observed sub-circuit.  A term is a Pauli word such as "X0X1" or "Z3"; its sub-circuit is what
+// XACC's observe() appends: H for X, Rx(pi/2) for Y, nothing for Z, then Measure on every qubit of the word.
+std::vector<double> executeVqe(std::shared_ptr<tnqvm::TNQVMVisitor> visitor, const HeterogeneousMap& options, std::shared_ptr<AcceleratorBuffer> buffer,
+                               std::shared_ptr<CompositeInstruction> ansatz, const std::vector<std::string>& terms, int shots) {
+  if (!visitor->supportVqeMode()) xacc::error("visitor does not support VQE mode");
+  visitor->setOptions(options);
+  if (visitor->name() == "exatn-mps") nearestNeighborTransform(ansatz, 1);
+  visitor->initialize(buffer, shots);
+  visitor->setKernelName(ansatz->name());
+  InstructionIterator it(ansatz);
+  while (it.hasNext()) {
+    auto inst = it.next();
+    if (inst->isEnabled()) inst->accept(visitor);
+  }
+  std::vector<double> out;
+  for (const auto& term : terms) {
+    auto obs = std::make_shared<CompositeInstruction>(term);
+    std::vector<std::size_t> measured;
+    for (size_t i = 0; i < term.size();) {
+      const char pauli = term[i++];
+      size_t j = i;
+      while (j < term.size() && isdigit((unsigned char)term[j])) ++j;
+      if (j == i || (pauli != 'X' && pauli != 'Y' && pauli != 'Z')) xacc::error("cannot parse observable term: " + term);
+      const std::size_t q = (std::size_t)atoi(term.substr(i, j - i).c_str());
+      i = j;
+      if (pauli == 'X') obs->addInstruction(createInstruction("H", {q}));
+      if (pauli == 'Y') obs->addInstruction(createInstruction("Rx", {q}, {InstructionParameter(M_PI / 2)}));
+      measured.push_back(q);
+    }
+    for (auto q : measured) obs->addInstruction(createInstruction("Measure", {q}));
+    out.push_back(visitor->getExpectationValueZ(obs));
+  }
+  visitor->finalize();
+  return out;
+}
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -142,7 +179,7 @@ int main(int argc, char** argv) {
   int nq = 0, shots = -1, maxBond = 0, seed = -1, device = 0, gauge = 0;
   double cutoff = -1.0;
   bool wantState = false, dumpNN = false, fuse2q = false;
-  std::string bitstring;
+  std::string bitstring, observe;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     auto next = [&]() { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return std::string(argv[++i]); };
@@ -158,7 +195,8 @@ int main(int argc, char** argv) {
     else if (a == "--dump-nn") dumpNN = true;   // print the nearest-neighbourised program and exit (no GPU needed)
     else if (a == "--bitstring") bitstring = next();
     else if (a == "--fuse-2q") fuse2q = true;
-    else { fprintf(stderr, "usage: b200_tnqvm_run --xasm FILE|- [--qubits N] [--shots S] [--max-bond-dim D] [--svd-cutoff E] [--seed K] [--state] [--bitstring 01x1..] [--fuse-2q]\n"); return 2; }
+    else if (a == "--observe") observe = next();   // VQE mode: semicolon-separated Pauli words, e.g. "X0X1;Y0Y1;Z0;Z1"
+    else { fprintf(stderr, "usage: b200_tnqvm_run --xasm FILE|- [--qubits N] [--shots S] [--max-bond-dim D] [--svd-cutoff E] [--seed K] [--state] [--bitstring 01x1..] [--fuse-2q] [--observe \"X0X1;Z0\"]\n"); return 2; }
   }
   try {
     std::stringstream ss;
@@ -194,7 +232,14 @@ int main(int argc, char** argv) {
     auto visitor = std::make_shared<tnqvm::B200MpsVisitor>();
     auto buffer = std::make_shared<AcceleratorBuffer>("q", nq);
     const int nInst = kernel->nInstructions();
-    execute(visitor, opts, buffer, kernel, shots);
+    std::vector<double> vqeTerms;
+    if (!observe.empty()) {
+      std::vector<std::string> terms;
+      std::stringstream ts(observe);
+      for (std::string t; std::getline(ts, t, ';');) if (!t.empty()) terms.push_back(t);
+      vqeTerms = executeVqe(visitor, opts, buffer, kernel, terms, shots);
+    } else
+      execute(visitor, opts, buffer, kernel, shots);
     printf("{\"visitor\": \"%s\", \"qubits\": %d, \"instructions\": %d, \"instructions_after_nn\": %d", visitor->name().c_str(), nq, nInst,
            kernel->nInstructions());
     for (auto& kv : buffer->getInformation())
@@ -213,6 +258,11 @@ int main(int argc, char** argv) {
       const auto& im = std::get<std::vector<double>>((*buffer)["amplitude-imag-vec"]);
       printf(", \"amplitude_slice\": [");
       for (size_t i = 0; i < re.size(); ++i) printf("%s[%.17g, %.17g]", i ? ", " : "", re[i], im[i]);
+      printf("]");
+    }
+    if (!observe.empty()) {
+      printf(", \"vqe_terms\": [");
+      for (size_t i = 0; i < vqeTerms.size(); ++i) printf("%s%.17g", i ? ", " : "", vqeTerms[i]);
       printf("]");
     }
     if (wantState) {

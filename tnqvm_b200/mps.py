@@ -78,6 +78,16 @@ class B200MPS:
     def reset(self):
         self._ck(self.L.mps_reset(self.h))
 
+    def snapshot(self):
+        """Remember the current state on the device (VQE mode: the ansatz state, TNQVM.cpp:52-92)."""
+        self._ck(self.L.mps_snapshot(self.h))
+
+    def restore(self):
+        self._ck(self.L.mps_restore(self.h))
+
+    def clear_measure(self):
+        self._ck(self.L.mps_clear_measure(self.h))
+
     # ---- gates
     def apply_1q(self, q, m):
         m = np.ascontiguousarray(m, dtype=np.complex128)
