@@ -154,3 +154,96 @@ def study(chi, gauge=0, n=None, depth=None):
                 if 2 * b > T.shape[1]: continue
                 s, hist = block_jacobi_fast(T, b=b, qr=qr)
                 print("  qr=%d b=%2d nb=%2d: outer sweeps %2d hist %s relerr %.1e" % (qr, b, T.shape[1] // b, len(hist), hist, np.max(np.abs(s - sref)) / sref[0]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Orderings for the block tournament.  Each returns the list of steps of ONE sweep; a step
+# is a perfect matching [(A, B), ...] of the nbe blocks.
+def order_round_robin(nbe):
+    steps = []
+    for step in range(nbe - 1):
+        st = []
+        for pi in range(nbe // 2):
+            if pi == 0: st.append((nbe - 1, step))
+            else: st.append(((step + pi) % (nbe - 1), (step + nbe - 1 - pi) % (nbe - 1)))
+        steps.append(st)
+    return steps
+
+
+def order_resident(nbe):
+    """Recursive bipartite tournament (nbe a power of two): split the blocks into halves R and T; for m = |R| steps pair
+    R_i with T_(i+s) -- block R_i never leaves its task (it can stay in shared memory), the T blocks stream past; then both
+    halves recurse concurrently.  nbe - 1 steps per sweep, every step a perfect matching, every pair once."""
+    assert nbe & (nbe - 1) == 0
+    def rec(groups):
+        m = len(groups[0]) // 2
+        if m == 0:
+            return []
+        steps = []
+        for s in range(m):
+            st = []
+            for g in groups:
+                R, T = g[:m], g[m:]
+                st += [(R[i], T[(i + s) % m]) for i in range(m)]
+            steps.append(st)
+        return steps + rec([h for g in groups for h in (g[:m], g[m:])])
+    return rec([list(range(nbe))])
+
+
+def block_jacobi_order(T, steps_of_sweep, b=8, tol=None, max_outer=60):
+    """One-sided block Jacobi with the cross-pairs-only rule of the kernel: the pairs inside a block are rotated at the first
+    step of a sweep only (`within`), every later step rotates the 64 cross pairs of its two blocks (one cyclic pass)."""
+    M, N = T.shape
+    X = T.copy()
+    tol = tol or math.sqrt(M) * 2.2e-16
+    fro2 = np.linalg.norm(X) ** 2
+    dead = (10 * tol) ** 2 * fro2 / N
+    hist = []
+    for sweep in range(max_outer):
+        dirty = 0
+        for si, st in enumerate(steps_of_sweep):
+            for (A_, B_) in st:
+                cols = list(range(A_ * b, A_ * b + b)) + list(range(B_ * b, B_ * b + b))
+                Xs = X[:, cols]
+                W = Xs.conj().T @ Xs
+                Q = np.eye(2 * b, dtype=complex)
+                rot = 0
+                pairs = [(p, q) for p in range(b) for q in range(b, 2 * b)]
+                if si == 0:
+                    pairs = [(p, q) for p in range(2 * b) for q in range(p + 1, 2 * b)]
+                for (p, q) in pairs:
+                    a, c, g = W[p, p].real, W[q, q].real, W[p, q]
+                    g2 = abs(g) ** 2
+                    if a > dead and c > dead and g2 > tol * tol * a * c:
+                        d = c - a
+                        h = math.sqrt(d * d + 4 * g2)
+                        u = (2.0 if d >= 0 else -2.0) / (abs(d) + h)
+                        cs = 1 / math.sqrt(1 + u * u * g2)
+                        sg = cs * u * g
+                        J = np.array([[cs, sg], [-np.conj(sg), cs]])
+                        W[:, [p, q]] = W[:, [p, q]] @ J
+                        W[[p, q], :] = J.conj().T @ W[[p, q], :]
+                        Q[:, [p, q]] = Q[:, [p, q]] @ J
+                        rot += 1
+                if rot:
+                    dirty += 1
+                    X[:, cols] = Xs @ Q
+        hist.append(dirty)
+        if dirty == 0:
+            break
+    s = np.sort(np.linalg.norm(X, axis=0))[::-1]
+    return s, hist
+
+
+def study_orderings(chi=64, n=16, depth=20, count=4):
+    ths = thetas(n=n, depth=depth, chi=chi, seed=3)
+    print("chi", chi, "thetas", len(ths), ths[0].shape)
+    for T in ths[-count:]:
+        sref = np.linalg.svd(T, compute_uv=False)
+        X = np.linalg.qr(T, mode='r').conj().T.copy()
+        nbe = X.shape[1] // 8
+        for name, order in (("round_robin", order_round_robin), ("resident", order_resident)):
+            steps = order(nbe)
+            assert len(steps) == nbe - 1 and len({tuple(sorted(p)) for st in steps for p in st}) == nbe * (nbe - 1) // 2
+            s, hist = block_jacobi_order(X, steps)
+            print("  %-12s sweeps %2d  dirty tasks per sweep %s  relerr %.1e" % (name, len(hist), hist, np.max(np.abs(s - sref)) / sref[0]))
