@@ -247,3 +247,68 @@ def study_orderings(chi=64, n=16, depth=20, count=4):
             assert len(steps) == nbe - 1 and len({tuple(sorted(p)) for st in steps for p in st}) == nbe * (nbe - 1) // 2
             s, hist = block_jacobi_order(X, steps)
             print("  %-12s sweeps %2d  dirty tasks per sweep %s  relerr %.1e" % (name, len(hist), hist, np.max(np.abs(s - sref)) / sref[0]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Mixed precision: complex64 sweeps that accumulate V, V re-unitarised in complex128 by
+# Newton-Schulz, G V formed in complex128, complex128 polishing sweeps.  How many polishing sweeps remain?
+def fp32_presweeps(G, b=8, max_outer=12):
+    M, N = G.shape
+    X = G.astype(np.complex64)
+    V = np.eye(N, dtype=np.complex64)
+    tol = np.float32(math.sqrt(M) * 6e-8)
+    nbe = N // b
+    steps = order_round_robin(nbe)
+    hist = []
+    for sweep in range(max_outer):
+        dirty = 0
+        for si, st in enumerate(steps):
+            for (A_, B_) in st:
+                cols = list(range(A_ * b, A_ * b + b)) + list(range(B_ * b, B_ * b + b))
+                Xs = X[:, cols]
+                W = (Xs.conj().T @ Xs).astype(np.complex64)
+                Q = np.eye(2 * b, dtype=np.complex64)
+                rot = 0
+                pairs = [(p, q) for p in range(b) for q in range(b, 2 * b)] if si else [(p, q) for p in range(2 * b) for q in range(p + 1, 2 * b)]
+                for (p, q) in pairs:
+                    a, c, g = np.float32(W[p, p].real), np.float32(W[q, q].real), W[p, q]
+                    g2 = np.float32(abs(g) ** 2)
+                    if g2 > tol * tol * a * c:
+                        d = np.float32(c - a)
+                        h = np.float32(math.sqrt(d * d + 4 * g2))
+                        u = np.float32((2.0 if d >= 0 else -2.0) / (abs(d) + h))
+                        cs = np.float32(1 / math.sqrt(1 + u * u * g2))
+                        sg = np.complex64(cs * u * g)
+                        J = np.array([[cs, sg], [-np.conj(sg), cs]], dtype=np.complex64)
+                        W[:, [p, q]] = W[:, [p, q]] @ J
+                        W[[p, q], :] = J.conj().T @ W[[p, q], :]
+                        Q[:, [p, q]] = Q[:, [p, q]] @ J
+                        rot += 1
+                if rot:
+                    dirty += 1
+                    X[:, cols] = Xs @ Q
+                    V[:, cols] = V[:, cols] @ Q
+        hist.append(dirty)
+        if dirty == 0:
+            break
+    return V, hist
+
+
+def study_mixed(chi=64, n=16, depth=20, count=3):
+    ths = thetas(n=n, depth=depth, chi=chi, seed=3)
+    for T in ths[-count:]:
+        sref = np.linalg.svd(T, compute_uv=False)
+        G = np.linalg.qr(T, mode='r').conj().T.copy()
+        N = G.shape[1]
+        steps = order_round_robin(N // 8)
+        _, h64 = block_jacobi_order(G, steps)
+        for pre in (6, 8, 12):
+            V32, h32 = fp32_presweeps(G, max_outer=pre)
+            V = V32.astype(np.complex128)
+            u0 = np.linalg.norm(V.conj().T @ V - np.eye(N))
+            for _ in range(2):
+                V = V @ (1.5 * np.eye(N) - 0.5 * (V.conj().T @ V))
+            u2 = np.linalg.norm(V.conj().T @ V - np.eye(N))
+            s, hp = block_jacobi_order(G @ V, steps)
+            print("fp64 only: %d sweeps | fp32 pre-sweeps %2d %s  unitarity %.1e -> %.1e | fp64 polish sweeps %d %s  relerr %.1e"
+                  % (len(h64), len(h32), h32[-3:], u0, u2, len(hp), hp, np.max(np.abs(s - sref)) / sref[0]))
