@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 import reference_cases as RC
+from oracle import oracle as O   # checker only
 from tnqvm_b200 import circuits as Cc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -141,6 +142,9 @@ def test_visitor_vqe_mode_one_ansatz_many_terms():
         circ += [("Measure", (q,), ()) for _, q in ops]
         one = json.loads(run(circ, n))
         assert abs(one["exp-val-z"] - val) < 1e-10, t
+        # and the reference's own dense simulator (oracle/_ref: Gates.hpp + GateMatrixAlgebra.hpp) on the same term
+        dense = O.dense_run(n, [g for g in circ if g[0] != "Measure"])
+        assert abs(O.dense_expval_z(dense, n, [q for _, q in ops]) - val) < 1e-10, t
     base = json.loads(run(ansatz, n, "--state"))
     sv = np.array([complex(a, b) for a, b in res["state"]])
     sv0 = np.array([complex(a, b) for a, b in base["state"]])
