@@ -358,7 +358,9 @@ struct mps_b200_handle {
     ensure_ws(bytes + 256);
     ws.reset();
     size_t o = ws.reserve(bytes);
-    char* st = pinned(0, bytes);
+    // staging region 1, not 0: run_layer fills region 0 with its descriptors right after this call, while this upload may
+    // still be in flight; region 1 is only ever written after a stream synchronisation (here and after the sweeps)
+    char* st = pinned(1, bytes);
     CK(cudaStreamSynchronize(stream));   // staging reuse safety (1q-only flushes are rare)
     memcpy(st, p1.data(), bytes);
     CK(cudaMemcpyAsync(ws.base + o, st, bytes, cudaMemcpyHostToDevice, stream));
