@@ -21,7 +21,7 @@
 namespace mpsb200 {
 namespace {
 
-constexpr int JT = 128;     // threads per CTA (4 warps)
+constexpr int JT = 128;     // threads per CTA of the 4-warp pair task (the 8-warp variant launches 256)
 constexpr int WLD = 17;     // padded leading dimension of the 16x16 shared matrices
 __device__ unsigned long long g_phase_cycles[8];   // developer timing (g_dbg_mode == 10): A, reduce+test, B, C, wait, tasks
 __device__ unsigned long long g_dmma_flops = 0;   // real flops executed on the DMMA pipe by the pair tasks (reporting only)
@@ -233,7 +233,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   if (tid == 0) atomicAdd(&g_dmma_flops, (unsigned long long)((M + 3) >> 2) * (within ? 5120ull : 2048ull) + (unsigned long long)((M + 7) >> 3) * (M3 ? 12288ull : 16384ull));
   if (tid == 0) dirty[mat] = 1;
 
-  // ------------------------------------------------------------------ phase B: Jacobi rotations on W (all four warps)
+  // ------------------------------------------------------------------ phase B: Jacobi rotations on W (warps 0-3; warps 4-7 of an 8-warp task only take the barriers)
   // Round r rotates 8 disjoint column pairs.  Rounds 0-7 are the bipartite schedule over the cross pairs (i, 8 + (i+r)%8);
   // rounds 8-14 (only when `within`: the first step of a tournament) are the two 8-column round-robins of the pairs
   // inside each block, which every later step of the sweep leaves alone.  Lanes 0-7 of warp 0 compute the rotations
