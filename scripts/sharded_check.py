@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--depth", type=int, default=16)
     ap.add_argument("--chi", type=int, default=128)
     ap.add_argument("--seed", type=int, default=9)
+    ap.add_argument("--partition-by", default="count", choices=["count", "cost"])
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -34,7 +35,7 @@ def main():
 
     out = {}
     for rep in range(2):   # first pass warms NCCL connections and allocations
-        sm = sharded.ShardedMPS(a.qubits, max_bond=a.chi, device=local)
+        sm = sharded.ShardedMPS(a.qubits, max_bond=a.chi, device=local, partition_by=a.partition_by)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         sm.run(circ)
@@ -59,7 +60,7 @@ def main():
             t_1 = time.perf_counter() - t0
             z_1, nrm_1 = e.expval_z_all(), e.norm()
             e.close()
-        out = {"check": "site_sharded_vs_single_gpu", "n_gpus": world, "qubits": a.qubits, "depth": a.depth, "max_bond_dim": a.chi,
+        out = {"check": "site_sharded_vs_single_gpu", "n_gpus": world, "partition_by": a.partition_by, "qubits": a.qubits, "depth": a.depth, "max_bond_dim": a.chi,
                "gates_2q": n2, "max_abs_dz": float(np.abs(z_sh - z_1).max()), "abs_dnorm": float(abs(nrm_sh - nrm_1)),
                "wall_ms_sharded": t_sh * 1e3, "wall_ms_single_gpu": t_1 * 1e3, "speedup": t_1 / t_sh,
                "boundary_exchanges": int(tot[0].item()), "bytes_over_nvlink": int(tot[1].item())}

@@ -64,10 +64,10 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, circ, max_bond, q):
+def _worker(rank, world, port, n, circ, max_bond, q, partition_by="count"):
     try:
         dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
-        sh = S.ShardedMPS(n, max_bond=max_bond, local_factory=lambda ns, **kw: OracleLocal(ns, **kw))
+        sh = S.ShardedMPS(n, max_bond=max_bond, local_factory=lambda ns, **kw: OracleLocal(ns, **kw), partition_by=partition_by)
         sh.run(circ)
         full = sh.gather_to_root()
         if rank == 0:
@@ -82,11 +82,11 @@ def _worker(rank, world, port, n, circ, max_bond, q):
         q.put(("err", "rank %d: %s\n%s" % (rank, e, traceback.format_exc())))
 
 
-def _run_sharded(world, n, circ, max_bond):
+def _run_sharded(world, n, circ, max_bond, partition_by="count"):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    ps = [ctx.Process(target=_worker, args=(r, world, port, n, circ, max_bond, q)) for r in range(world)]
+    ps = [ctx.Process(target=_worker, args=(r, world, port, n, circ, max_bond, q, partition_by)) for r in range(world)]
     for p in ps:
         p.start()
     res = [q.get(timeout=240) for _ in ps]
@@ -191,3 +191,31 @@ def test_parameter_sweep_sharded_across_ranks():
         for i, c in enumerate(circs):
             ref = O.OracleMPS(n).run(c)
             assert np.allclose(out[i], [ref.expval_z([k]) for k in range(n)], atol=1e-12)
+
+
+def test_cost_balanced_partition():
+    """balance the blocks by the SVD work of the saturated bond profile, not by site count."""
+    def cost(n, chi, bounds):
+        dims = [1] + [min(chi, 2 ** min(k + 1, n - 1 - k)) for k in range(n - 1)] + [1]
+        w = [0.0 if k == n - 1 else (2.0 * dims[k]) * (2.0 * dims[k + 2]) * min(2.0 * dims[k], 2.0 * dims[k + 2]) for k in range(n)]
+        return [sum(w[s:e]) for s, e in bounds]
+    for n, world, chi in ((50, 4, 256), (50, 8, 256), (100, 8, 512), (53, 8, 1024), (10, 4, 4), (5, 4, 2), (4, 4, 64)):
+        b = S.partition(n, world, chi)
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        assert all(e > s for s, e in b)
+        if n >= 50:
+            even = S.partition(n, world)
+            assert max(cost(n, chi, b)) < 0.9 * max(cost(n, chi, even))      # the heaviest block got lighter
+            assert b[0][1] - b[0][0] > even[0][1] - even[0][0]               # because the cheap chain ends got more sites
+    assert S.partition(50, 4, 0) == S.partition(50, 4) and S.partition(50, 1, 256) == [(0, 50)]
+
+
+def test_site_sharded_cost_partition_equals_single_process():
+    from oracle import oracle as O
+    n, world, chi = 11, 3, 4
+    assert S.partition(n, world, chi) != S.partition(n, world)
+    circ = Cc.brickwork(n, 6, seed=3, prefix_ghz=True)
+    ok, _ = _run_sharded(world, n, circ, chi, partition_by="cost")
+    ref = O.OracleMPS(n, max_bond=chi).run(circ)
+    assert np.max(np.abs(np.array(ok[1]) - np.array([ref.expval_z([k]) for k in range(n)]))) < 1e-9
+    assert abs(ok[2] - ref.norm()) < 1e-9 and ok[3] == ref.bond_dims().tolist()

@@ -21,14 +21,42 @@ import torch.distributed as dist
 from .mps import B200MPS
 
 
-def partition(n_sites, world):
-    """Contiguous site blocks [start, end) per rank; the first n % world ranks get one extra site."""
+def partition(n_sites, world, max_bond=0):
+    """Contiguous site blocks [start, end) per rank.  max_bond = 0: equal counts, the first n % world ranks get one extra
+    site.  max_bond > 0: blocks of equal estimated gate cost (balance by sum chi^3, not by site
+    count) -- a gate on bond k is charged to the owner of site k (the left owner executes boundary gates) with the SVD
+    cost M N min(M, N) of its theta on the saturated bond profile min(max_bond, 2^k, 2^(n-k)); the chain ends are cheap,
+    so the end ranks get more sites.  Every rank computes the same bounds from (n_sites, world, max_bond) alone."""
     if world < 1 or n_sites < world:
         raise ValueError("need at least one site per rank (n_sites=%d, world=%d)" % (n_sites, world))
-    base, rem = divmod(n_sites, world)
-    out, s = [], 0
+    if max_bond <= 0 or world == 1:
+        base, rem = divmod(n_sites, world)
+        out, s = [], 0
+        for r in range(world):
+            e = s + base + (1 if r < rem else 0)
+            out.append((s, e))
+            s = e
+        return out
+    dims = [1] + [min(max_bond, 2 ** min(k + 1, n_sites - 1 - k, 60)) for k in range(n_sites - 1)] + [1]   # dims[k] = bond left of site k
+    w = []
+    for k in range(n_sites):
+        if k == n_sites - 1:
+            w.append(0.0)
+        else:
+            m, n = 2.0 * dims[k], 2.0 * dims[k + 2]
+            w.append(m * n * min(m, n))
+    total = sum(w)
+    out, s, acc = [], 0, 0.0
     for r in range(world):
-        e = s + base + (1 if r < rem else 0)
+        if r == world - 1:
+            e = n_sites
+        else:
+            e = s + 1
+            acc += w[s]
+            # extend the block while that brings the running total closer to (r + 1) / world of the whole
+            while e < n_sites - (world - 1 - r) and abs(acc + w[e] - total * (r + 1) / world) <= abs(acc - total * (r + 1) / world):
+                acc += w[e]
+                e += 1
         out.append((s, e))
         s = e
     return out
@@ -88,12 +116,16 @@ class ShardedMPS:
     owns.  A 2q gate on a block boundary is executed by the LEFT owner, which keeps one ghost slot after its
     last site for the neighbour's boundary tensor."""
 
-    def __init__(self, n_qubits, max_bond=0, svd_cutoff=-1.0, gauge=0, group=None, local_factory=None, device=None, **options):
+    def __init__(self, n_qubits, max_bond=0, svd_cutoff=-1.0, gauge=0, group=None, local_factory=None, device=None,
+                 partition_by="count", **options):
         self.n = n_qubits
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        self.bounds = partition(n_qubits, self.world)
+        if partition_by not in ("count", "cost"):
+            raise ValueError("partition_by must be 'count' or 'cost'")
+        # "cost" balances the estimated SVD work of a saturated chain (needs max_bond); "count" is what profiles/ were measured with
+        self.bounds = partition(n_qubits, self.world, max_bond if partition_by == "cost" else 0)
         self.s, self.e = self.bounds[self.rank]
         self.nl = self.e - self.s
         self.has_ghost = self.rank < self.world - 1
