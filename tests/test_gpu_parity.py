@@ -104,15 +104,14 @@ def test_golden_fixtures_on_gpu():
         e.close()
 
 
-@pytest.mark.parametrize("opts", [dict(qr_prereduce=0), dict(jacobi_persistent=0), dict(jacobi_persistent=0, jacobi_groups=3),
-                                  dict(qr_prereduce=0, jacobi_persistent=0), dict(discard_margin=1e-12), dict(qr_lookahead=1),
-                                  dict(jacobi_3m=1), dict(jacobi_block16=1), dict(jacobi_wide_tasks=0, jacobi_ctas_per_sm=4),
-                                  dict(jacobi_wide_tasks=1, jacobi_ctas_per_sm=2), dict(jacobi_wide_tasks=0, jacobi_ctas_per_sm=1)],
-                         ids=["no_qr", "step_kernels", "stream_groups", "no_qr_step_kernels", "discard_rule", "qr_lookahead", "jacobi_3m",
-                              "block16", "narrow_tasks_4_per_sm", "wide_tasks_2_per_sm", "narrow_tasks_1_per_sm"])
+@pytest.mark.parametrize("opts", [dict(qr_prereduce=0), dict(jacobi_wide_tasks=0, jacobi_ctas_per_sm=4),
+                                  dict(jacobi_wide_tasks=1, jacobi_ctas_per_sm=2), dict(jacobi_wide_tasks=0, jacobi_ctas_per_sm=1),
+                                  dict(jacobi_chunk_mb=1, l2_persist=0), dict(jacobi_chunk_mb=1, l2_persist=1)],
+                         ids=["no_qr", "narrow_tasks_4_per_sm", "wide_tasks_2_per_sm", "narrow_tasks_1_per_sm", "chunked_no_window",
+                              "chunked_l2_window"])
 def test_svd_engine_variants_agree_with_oracle(O, opts):
-    """Every SVD configuration (QR pre-reduction on/off, persistent dataflow sweep vs one launch per step, stream groups,
-    discard-aware rule) must give the reference's observables: exact run at 1e-10, truncated run at TRUNC_TOL."""
+    """Every SVD configuration (QR pre-reduction on/off, resident CTAs / warps per pair task, one chunk per layer vs many
+    chunks, persisting-L2 window on/off) must give the reference's observables: exact run at 1e-10, truncated at TRUNC_TOL."""
     n = 14
     circ = Cc.brickwork(n, 10, seed=21, prefix_ghz=True)
     for chi, tol in ((0, EXACT_TOL), (16, TRUNC_TOL)):
@@ -125,8 +124,6 @@ def test_svd_engine_variants_agree_with_oracle(O, opts):
         assert abs(e.expval_z([0, n - 1]) - o.expval_z([0, n - 1])) < tol
         if chi == 0:
             assert np.abs(e.statevector() - o.statevector()).max() < tol
-        if "jacobi_3m" in opts:
-            e.set_option("jacobi_3m", 0)   # process-wide switch: restore the default
         e.close()
 
 

@@ -12,7 +12,9 @@ Reference shapes restated here (nothing is copied):
     tnqvm/TNQVM.cpp:119-124): tnqvm/visitors/exatn-mps/NearestNeighborTransform.hpp:43-135
   * Sycamore XASM input: examples/sycamore/resources/*.xasm (Rx/Ry/Rz/fSim)
 """
+import ast
 import math
+import operator
 import re
 
 import numpy as np
@@ -153,6 +155,33 @@ def sycamore_grid(depth=14, rows=9, cols=6, n=53, seed=0):
 _GATE_RE = re.compile(r"^\s*([A-Za-z0-9_]+)\s*\((.*)\)\s*;\s*$")
 
 
+_BINOPS = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.Div: operator.truediv, ast.Pow: operator.pow}
+
+
+def _eval_param(expr):
+    """Gate parameter of an XASM line: numbers, `pi`, + - * / ** and parentheses only (a whitelisted walk over the
+    parsed expression -- never eval(): a .xasm file is untrusted input)."""
+    def ev(node):
+        if isinstance(node, ast.Expression):
+            return ev(node.body)
+        if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)) and not isinstance(node.value, bool):
+            return float(node.value)
+        if isinstance(node, ast.Name) and node.id in ("pi", "PI", "M_PI"):
+            return math.pi
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.UAdd, ast.USub)):
+            v = ev(node.operand)
+            return -v if isinstance(node.op, ast.USub) else v
+        if isinstance(node, ast.BinOp) and type(node.op) in _BINOPS:
+            return float(_BINOPS[type(node.op)](ev(node.left), ev(node.right)))
+        raise ValueError("unsupported expression in XASM gate parameter: %r" % expr)
+    if len(expr) > 200:
+        raise ValueError("XASM gate parameter too long")
+    try:
+        return ev(ast.parse(expr, mode="eval"))
+    except SyntaxError:
+        raise ValueError("cannot parse XASM gate parameter: %r" % expr) from None
+
+
 def load_xasm(text):
     """Parse the XASM subset used by the reference's tests and examples/sycamore/resources/*.xasm:
     one instruction per line, ``Gate(q[i](, q[j])(, param)*);``.  Returns (n_qubits_seen, circuit)."""
@@ -172,13 +201,32 @@ def load_xasm(text):
             if mq:
                 qs.append(int(mq.group(1)))
             elif a:
-                ps.append(float(eval(a, {"__builtins__": {}}, {"pi": math.pi})))
+                ps.append(_eval_param(a))
         if name == "CX":
             name = "CNOT"
         if qs:
             nq = max(nq, max(qs) + 1)
         circ.append((name, tuple(qs), tuple(ps)))
     return nq, circ
+
+
+def load_circuit_fixture(path):
+    """A circuit stored as data (tests/golden/circuits/*.json.gz, written by tests/golden/make_sycamore_fixture.py from the
+    reference's resource files): returns (n_qubits, circuit)."""
+    import gzip
+    import json
+    with gzip.open(path, "rb") as f:
+        doc = json.loads(f.read().decode())
+    return int(doc["n_qubits"]), [(g[0], tuple(int(q) for q in g[1]), tuple(float(p) for p in g[2])) for g in doc["circuit"]]
+
+
+def sycamore_53(depth=14):
+    """BASELINE config 5: the reference's examples/sycamore/resources/sycamore_53_<depth>_0.xasm (53 qubits, Rx/Ry/Rz + fSim,
+    coupler distances 1..10), from the committed fixture; route it with nearest_neighbor()."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "circuits",
+                        "sycamore_53_%d_0.json.gz" % depth)
+    return load_circuit_fixture(path)
 
 
 def to_xasm(circuit, name="kernel"):

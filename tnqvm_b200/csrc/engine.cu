@@ -82,6 +82,7 @@ struct mps_b200_handle {
   double cutoff = DBL_MIN;
   int gauge = 0, device = 0;
   int cutoff_on_sqrt = 0, fuse_1q = 1, renorm = 0, profile = 0, layer_batch = 1, use_qr = 1;
+  int norm_guard = 1;   // post-SVD sanity check of ExaTnMpsVisitor.cpp:1632-1661 (both factors must have 2-norm >= 1e-3)
   // fuse_2q: consecutive 2q gates on the same site pair (and the 1q gates between them) become one 4x4 before they reach
   // the GPU, e.g. CX.Rz.CX = ZZ(gamma) of the QAOA circuits or Swap.Swap = 1 between two routed gates.
   // Off by default: the reference truncates after every 2q gate (ExaTnMpsVisitor.cpp:1394-1630), so with truncation
@@ -119,27 +120,21 @@ struct mps_b200_handle {
   char* pin_rb = nullptr;
   size_t pin_rb_cap = 0;
   cudaEvent_t ev[6] = {};
-  // Jacobi groups: the matrices of a layer are split over NGROUP streams so that the Gram / rotate / apply phases of
-  // different groups overlap on the SMs (one stream alone leaves the DMMA pipe idle during the serial rotation phase)
-  static constexpr int NGROUP = 4, GDEPTH = 2;
-  int jacobi_groups = 1;
-  int jacobi_persistent = 1;   // one persistent dataflow launch per sweep (jacobi_sweep_kernel) instead of one launch per step
+  cudaEvent_t sev[2] = {};   // Jacobi sweep read-backs (the host runs one sweep behind the device)
   int sm_count = 148;
   // persistent sweep kernel: resident CTAs per SM.  0 = by load: the routed circuits (configs 3 and 5) run layers of 2-8
   // gates, i.e. fewer pair tasks per tournament step than SMs x 4; launching only as many CTAs as there are tasks keeps
-  // such tasks one per SM instead of letting up to four of them share an SM's DMMA / FP64 pipes while other SMs idle
+  // such tasks one per SM instead of letting up to four of them share an SM's FP64 pipe while other SMs idle
   int ctas_per_sm = 0;
   int wide_tasks = 1;      // 8 warps per pair task when at most two tasks per SM are resident (0: always 4)
-  int jacobi_3m_on = 0;    // mirrors jacobi_set_3m (the 3M product exists for 4-warp tasks only)
-  int stagger_ns = 0;
-  int block16 = 0;   // Jacobi over 16-column blocks (32-column tasks): half the passes through L2 per sweep
-  double discard_margin = 0.0;    // discard-aware rotation rule: fraction of the keep-th largest squared column norm (0 = off)
-  cudaStream_t gstream[NGROUP] = {};
-  cudaEvent_t gev[NGROUP][GDEPTH] = {};
-  cudaEvent_t gend[NGROUP] = {}, gstart = nullptr;
-  int* pin_rem = nullptr;   // [NGROUP][GDEPTH] pinned
-  cudaEvent_t qev[4] = {};   // QR look-ahead (side stream = gstream[0], idle while the QR runs)
-  int qr_lookahead = 0;   // measured: the panel chain is the critical path, overlapping the trailing update buys nothing at chi=256
+  // Jacobi work matrices of one layer are processed in chunks whose total size fits this many MiB: a chunk stays
+  // L2-resident over its sweeps (126 MB L2) instead of streaming from HBM at every tournament step.  chi=256 layers
+  // (25 x 4 MiB) are one chunk, a chi=1024 theta (64 MiB) is a chunk of its own.
+  int chunk_mb = 96;
+  int l2_persist = 1;      // access-policy window (persisting L2 lines) over the Jacobi matrices of the running chunk
+  size_t l2_persist_max = 0, l2_window_max = 0;
+  double guard_violations = 0;   // norm-guard failures seen with norm_guard = 2
+  double nonconverged = 0;   // matrices that were still rotating after max_sweeps sweeps (truncated anyway; reported in mps_stats)
   // counters
   double n2q = 0, n1q = 0, nlayers = 0, nsweeps = 0, nlaunch = 0, ms_theta = 0, ms_svd = 0, ms_wb = 0, ms_qr = 0;
 
@@ -388,18 +383,10 @@ struct mps_b200_handle {
     run_1q(p1);
     if (g2.empty()) return;
     const int B = (int)g2.size();
-    const int NG = std::max(1, std::min({jacobi_groups, (int)NGROUP, B}));
-    if (NG > 1) {   // interleave the gates over the groups (chain ends are small, the middle is large): group g = b % NG
-      std::vector<int> r;
-      r.reserve(B);
-      for (int g = 0; g < NG; ++g)
-        for (int b = g; b < B; b += NG) r.push_back(g2[b]);
-      g2.swap(r);
-    }
     nlayers += 1;
     n2q += B;
 
-    struct Dim { int lo, cl, ch, cr, M, N, tall, Mg, Ng, Mj; size_t oT, oG, oY, oV, oTq, oCn2, oWd, oVer, oSig2, oSigma, oPerm, oSP, oSO, oKeep, oW; };
+    struct Dim { int lo, cl, ch, cr, M, N, tall, Mg, Ng, Mj; size_t oT, oG, oY, oV, oTq, oWd, oVer, oSig2, oSigma, oPerm, oSP, oSO, oKeep, oW; };
     std::vector<Dim> D(B);
     ws.reset();
     // pass 1: sizes
@@ -423,10 +410,9 @@ struct mps_b200_handle {
     const size_t oQr = ws.reserve(sizeof(QrProblem) * B);
     int pstride = 2;   // progress flags per matrix of the persistent sweep kernel: one per 8-column block
     for (int b = 0; b < B; ++b) pstride = std::max(pstride, ((D[b].Ng + 7) / 8 + 1) & ~1);
-    const size_t oProg = ws.reserve(sizeof(int) * ((size_t)B * pstride + max_sweeps + 4));
-    const size_t oThr = ws.reserve(sizeof(double) * B);   // discard-aware thresholds, zero = off (inside the zeroed block)
-    const size_t oActive = ws.reserve(sizeof(int) * (B + 2));   // matrices still rotating: [0] count, [1..] indices (uploaded as "all")
-    const size_t oFlags = ws.reserve(sizeof(int) * (2 * B + 4) + sizeof(double) * B + 16);   // dirty[B], done[B], remaining, pad, fro2[B]
+    const size_t oProg = ws.reserve(sizeof(int) * ((size_t)B * pstride + (size_t)(max_sweeps + 4) * (B + 1)));   // progress flags, then one task counter per (chunk, sweep)
+    const size_t oActive = ws.reserve(sizeof(int) * 2 * (B + 2));   // per chunk: [0] matrices still rotating, [1..] their indices (within the chunk)
+    const size_t oFlags = ws.reserve(sizeof(int) * (4 * B + 4) + sizeof(double) * B + 16);   // dirty[B], done[B], per chunk (remaining, fault), pad, fro2[B]
     const size_t oKeepBlk = ws.reserve((sizeof(int) + 2 * sizeof(double)) * B + 64);
     size_t sig_total = 0;
     for (int b = 0; b < B; ++b) sig_total += D[b].Ng;
@@ -441,10 +427,12 @@ struct mps_b200_handle {
         d.oW = oKeepBlk + ((sizeof(int) * B + 15) & ~size_t(15)) + 2 * sizeof(double) * b;
       }
     }
+    // the Jacobi work matrices of the layer are contiguous (one L2 access-policy window per chunk)
+    const size_t oGfirst = ws.reserve(0);
+    for (int b = 0; b < B; ++b) D[b].oG = ws.reserve(sizeof(double2) * (size_t)D[b].Mj * D[b].Ng);
     for (int b = 0; b < B; ++b) {
       Dim& d = D[b];
-      d.oCn2 = ws.reserve(sizeof(double) * d.Ng);
-      d.oWd = ws.reserve(sizeof(double2) * 256 * (size_t)((d.Ng + 15) / 16));   // >= 64 per 8-column block as well
+      d.oWd = ws.reserve(sizeof(double2) * 64 * (size_t)((d.Ng + 7) / 8 + 1));
       {
         const size_t nbe_ = (size_t)((((d.Ng + 7) / 8) + 1) & ~1);
         d.oVer = ws.reserve(sizeof(int) * nbe_ + 8 + sizeof(int2) * nbe_ * nbe_);   // versions, then the clean-pair memo
@@ -454,7 +442,6 @@ struct mps_b200_handle {
       d.oSP = ws.reserve(sizeof(double) * d.Ng);
       d.oSO = ws.reserve(sizeof(double) * d.Ng);
       d.oT = ws.reserve(sizeof(double2) * (size_t)d.Mg * d.Ng);
-      d.oG = ws.reserve(sizeof(double2) * (size_t)d.Mj * d.Ng);
       if (use_qr) {
         d.oY = ws.reserve(sizeof(double2) * (size_t)d.Mg * d.Ng);
         d.oV = ws.reserve(sizeof(double2) * 2 * (size_t)d.Mg * QR_PB);
@@ -465,8 +452,32 @@ struct mps_b200_handle {
     ensure_ws(total);
     char* wb = ws.base;
 
+    // Jacobi chunks: consecutive matrices whose work matrices fit `chunk_mb` together
+    struct Chunk { int c0, c1, pairs, steps; long tasks; size_t bytes; };
+    std::vector<Chunk> chunks;
+    {
+      const size_t budget = (size_t)std::max(1, chunk_mb) << 20;
+      for (int c0 = 0; c0 < B;) {
+        Chunk c{c0, c0, 1, 1, 0, 0};
+        while (c.c1 < B) {
+          const Dim& d = D[c.c1];
+          const size_t sz = sizeof(double2) * (size_t)d.Mj * d.Ng;
+          if (c.c1 > c0 && c.bytes + sz > budget) break;
+          c.bytes += sz;
+          const int nb = (d.Ng + 7) / 8, nbe = (nb == 1) ? 1 : ((nb + 1) & ~1);
+          const int np = nb == 1 ? 1 : nbe / 2;
+          c.pairs = std::max(c.pairs, np);
+          c.steps = std::max(c.steps, nb == 1 ? 1 : nbe - 1);
+          c.tasks += np;
+          ++c.c1;
+        }
+        chunks.push_back(c);
+        c0 = c.c1;
+      }
+    }
+
     // pass 2: descriptors
-    const size_t descBytes = oFlags + sizeof(int) * (2 * B + 4) + sizeof(double) * B + 16 - oGemm;
+    const size_t descBytes = oFlags + sizeof(int) * (4 * B + 4) + sizeof(double) * B + 16 - oGemm;
     char* st = pinned(0, descBytes);
     memset(st, 0, descBytes);
     GemmProblem* hG = (GemmProblem*)(st + (oGemm - oGemm));
@@ -474,7 +485,6 @@ struct mps_b200_handle {
     TruncProblem* hT = (TruncProblem*)(st + (oTr - oGemm));
     QrProblem* hQ = (QrProblem*)(st + (oQr - oGemm));
     int max_tiles = 0, max_pairs = 1, max_steps = 1, maxMg = 1, maxNg = 1;
-    long level_tasks = 0;   // pair tasks per tournament step over the whole layer
     for (int b = 0; b < B; ++b) {
       const QGate& g = queue[g2[b]];
       const Dim& d = D[b];
@@ -501,10 +511,9 @@ struct mps_b200_handle {
         q.Y = (double2*)(wb + d.oY); q.V = (double2*)(wb + d.oV); q.T = (double2*)(wb + d.oTq); q.G = j.G;
         q.M = d.Mg; q.N = d.Ng; q.ldy = d.Mg;
       }
-      const bool b16 = block16 && jacobi_persistent && NG == 1;
-      j.nb = b16 ? (d.Ng + 15) / 16 : (d.Ng + 7) / 8;
+      j.nb = (d.Ng + 7) / 8;
       j.nbe = (j.nb == 1) ? 1 : ((j.nb + 1) & ~1);
-      j.cn2 = (double*)(wb + d.oCn2); j.thr = (double*)(wb + oThr) + b; j.wd = (double2*)(wb + d.oWd);
+      j.wd = (double2*)(wb + d.oWd);
       {
         const size_t nbe_ = (size_t)((j.nb + 1) & ~1);
         j.ver = (int*)(wb + d.oVer);
@@ -512,7 +521,6 @@ struct mps_b200_handle {
         CK(cudaMemsetAsync(wb + d.oVer, 0, sizeof(int) * nbe_ + 8 + sizeof(int2) * nbe_ * nbe_, stream));
       }
       max_pairs = std::max(max_pairs, j.nb == 1 ? 1 : j.nbe / 2);
-      level_tasks += (j.nb == 1 ? 1 : j.nbe / 2);
       max_steps = std::max(max_steps, j.nb == 1 ? 1 : j.nbe - 1);
       maxMg = std::max(maxMg, d.Mg);
       maxNg = std::max(maxNg, d.Ng);
@@ -523,16 +531,16 @@ struct mps_b200_handle {
       t.scaleP = (double*)(wb + d.oSP); t.scaleO = (double*)(wb + d.oSO);
       t.keep = (int*)(wb + d.oKeep); t.weights = (double*)(wb + d.oW);
     }
-    {
-      int* ha = (int*)(st + (oActive - oGemm));
-      ha[0] = B;
-      for (int b = 0; b < B; ++b) ha[1 + b] = b;
+    for (size_t k = 0; k < chunks.size(); ++k) {   // per chunk: "all its matrices rotating" (indices within the chunk)
+      int* ha = (int*)(st + (oActive - oGemm)) + (chunks[k].c0 + 2 * k);
+      ha[0] = chunks[k].c1 - chunks[k].c0;
+      for (int b = 0; b < ha[0]; ++b) ha[1 + b] = b;
     }
     CK(cudaMemcpyAsync(wb + oGemm, st, descBytes, cudaMemcpyHostToDevice, stream));   // flags zeroed too
     int* d_dirty = (int*)(wb + oFlags);
     int* d_done = d_dirty + B;
-    int* d_rem = d_done + B;
-    double* d_fro2 = (double*)(wb + oFlags + ((sizeof(int) * (2 * B + 4) + 7) & ~size_t(7)));
+    int* d_rem = d_done + B;   // per chunk c: d_rem[2c] = matrices still rotating, d_rem[2c+1] = dataflow faults
+    double* d_fro2 = (double*)(wb + oFlags + ((sizeof(int) * (4 * B + 4) + 7) & ~size_t(7)));
 
     if (profile) CK(cudaEventRecord(ev[0], stream));
     launch_gemm((const GemmProblem*)(wb + oGemm), B, max_tiles, 0, stream);
@@ -541,7 +549,7 @@ struct mps_b200_handle {
 
     // ---- QR pre-reduction: theta_o = Q R, the Jacobi runs on G = R^H
     if (use_qr) {
-      launch_qr((const QrProblem*)(wb + oQr), B, maxMg, maxNg, stream, qr_lookahead ? gstream[0] : nullptr, qr_lookahead ? qev : nullptr);
+      launch_qr((const QrProblem*)(wb + oQr), B, maxMg, maxNg, stream);
       nlaunch += qr_launch_count(maxNg);
       CK(cudaGetLastError());
     }
@@ -553,105 +561,84 @@ struct mps_b200_handle {
     const double tol2 = tol * tol;
     const double ntol = null_tol > 0 ? null_tol : 10.0 * tol;   // numerically-null threshold relative to sigma_max
     const double dead2 = ntol * ntol;
-    int* h_rem = (int*)pinned_rb(sizeof(int) * (B + 4) + sizeof(double) * (2 * B + sig_total) + 256);
+    const size_t remBytes = (sizeof(int) * 2 * (size_t)(max_sweeps + 4) * chunks.size() + 255) & ~size_t(255);
+    int* h_rem = (int*)pinned_rb(remBytes + sizeof(int) * (B + 4) + sizeof(double) * (2 * B + sig_total) + 256);
     launch_fro2((const JacobiProblem*)(wb + oJac), B, d_fro2, stream);
     nlaunch += 1;
     int sweep = 0;
     static const bool trace = getenv("MPS_B200_TRACE") != nullptr;   // developer aid: per-sweep progress on stderr
-    if (jacobi_persistent && NG == 1) {
+    {
+      // Chunks: consecutive matrices whose work matrices fit `chunk_mb` together run their sweeps to convergence before the
+      // next chunk starts, so that a chunk is L2-resident across its sweeps.  Convergence is decided on the device
+      // (jacobi_check_kernel marks finished matrices, the sweep kernel skips them); the host only learns how many matrices
+      // are still rotating -- one sweep late: sweep k+1 is already queued when the count of sweep k is read, and a sweep
+      // over a finished chunk is an empty launch.  No stream synchronisation inside the loop.
       int* d_prog = (int*)(wb + oProg);
       int* d_cnt = d_prog + (size_t)B * pstride;
-      int* d_active = (int*)(wb + oActive);
-      if (trace) CK(cudaEventRecord(ev[5], stream));
-      int rotating = B;
-      for (; sweep < max_sweeps; ++sweep) {
-        int per_sm = ctas_per_sm, warps = 4;
-        {
+      const JacobiProblem* dJ = (const JacobiProblem*)(wb + oJac);
+      int nchunk = 0;
+      for (const Chunk& ck : chunks) {
+        const int c0 = ck.c0, c1 = ck.c1, cpairs = ck.pairs, csteps = ck.steps;
+        const long ctasks = ck.tasks;
+        const size_t bytes = ck.bytes;
+        const int CB = c1 - c0;
+        int* d_active = (int*)(wb + oActive) + (c0 + 2 * nchunk);
+        int* d_crem = d_rem + 2 * nchunk;
+        int* d_ccnt = d_cnt + (size_t)nchunk * (max_sweeps + 4);
+        const bool window = l2_persist && l2_window_max > 0 && true;
+        if (window) {
+          cudaStreamAttrValue av;
+          memset(&av, 0, sizeof(av));
+          av.accessPolicyWindow.base_ptr = wb + D[c0].oG;
+          av.accessPolicyWindow.num_bytes = std::min(bytes, l2_window_max);
+          av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)l2_persist_max / (double)std::max<size_t>(1, av.accessPolicyWindow.num_bytes));
+          av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+          av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+          CK(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+        }
+        int rotating = CB, csweep = 0, queued = 0, seen = 0;
+        volatile int* h_crem = (volatile int*)(h_rem + 2 * (size_t)(max_sweeps + 4) * nchunk);
+        auto enqueue = [&]() {
+          int per_sm = ctas_per_sm, warps = 4;
           // live tasks per tournament step (finished matrices have no slots: d_active); phantom slots of the smaller
-          // matrices of the layer still cost one dequeue each, so a CTA should not walk through more than ~100 per sweep
-          const long est = std::max<long>(1, level_tasks * rotating / B);
-          const long slots = (long)max_steps * rotating * max_pairs;
+          // matrices of the chunk still cost one dequeue each, so a CTA should not walk through more than ~100 per sweep
+          const long est = std::max<long>(1, ctasks * rotating / CB);
+          const long slots = (long)csteps * rotating * cpairs;
           const long want = std::max(est, slots / 96);
           if (per_sm <= 0) per_sm = (int)std::max<long>(1, std::min<long>(4, (want + sm_count - 1) / sm_count));
           // at most two tasks per SM: give each task eight warps (the register file holds 2 x 256 threads of this kernel)
-          if (wide_tasks && !jacobi_3m_on && per_sm <= 2) warps = 8;
+          if (wide_tasks && per_sm <= 2) warps = 8;
+          launch_jacobi_sweep(dJ + c0, rotating, cpairs, csteps, queued * csteps, tol2, dead2, d_fro2 + c0, d_dirty + c0, d_done + c0,
+                              d_prog + (size_t)c0 * pstride, pstride, d_ccnt + queued, d_crem + 1, sm_count * per_sm, warps, d_active, stream);
+          launch_jacobi_check(CB, d_dirty + c0, d_done + c0, d_crem, d_active, stream);
+          nlaunch += 2;
+          CK(cudaMemcpyAsync((void*)(h_crem + 2 * queued), d_crem, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+          CK(cudaEventRecord(sev[queued & 1], stream));
+          ++queued;
+        };
+        enqueue();
+        for (;;) {
+          if (queued < max_sweeps) enqueue();   // one sweep ahead of what the host has seen
+          CK(cudaEventSynchronize(sev[seen & 1]));
+          const int rem = h_crem[2 * seen], fault = h_crem[2 * seen + 1];
+          ++seen;
+          if (fault != 0) throw std::runtime_error("internal: Jacobi dataflow wait timed out");
+          if (trace) fprintf(stderr, "[mps_b200 trace] layer %d chunk %d (%d matrices) sweep %d: %d still rotating\n", (int)nlayers, nchunk, CB, seen - 1, rem);
+          if (rem == 0) { csweep = seen; break; }
+          rotating = std::min(CB, std::max(1, rem));
+          if (seen >= queued) { csweep = seen; nonconverged += rem; break; }   // max_sweeps reached with matrices still rotating
         }
-        if (block16)
-          launch_jacobi_sweep16((const JacobiProblem*)(wb + oJac), B, max_pairs, max_steps, sweep * max_steps, tol2, dead2, d_fro2,
-                                d_dirty, d_done, d_prog, pstride, d_cnt + sweep, d_rem + 1, sm_count, stream);
-        else
-        launch_jacobi_sweep((const JacobiProblem*)(wb + oJac), rotating, max_pairs, max_steps, sweep * max_steps, tol2, dead2, d_fro2, d_dirty,
-                            d_done, d_prog, pstride, d_cnt + sweep, d_rem + 1, sm_count * per_sm, warps, stagger_ns, d_active, stream);
-        launch_jacobi_check(B, d_dirty, d_done, d_rem, d_active, stream);
-        nlaunch += 2;
-        if (discard_margin > 0 && maxNg > max_bond) {
-          launch_jacobi_thr((const JacobiProblem*)(wb + oJac), B, max_bond, discard_margin, d_done, stream);
-          nlaunch += 1;
-        }
-        CK(cudaMemcpyAsync(h_rem, d_rem, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-        if (trace) CK(cudaEventRecord(ev[3], stream));
-        CK(cudaStreamSynchronize(stream));
-        if (h_rem[1] != 0) throw std::runtime_error("internal: Jacobi dataflow wait timed out");
-        if (trace) {
-          float ms = 0;
-          CK(cudaEventElapsedTime(&ms, ev[5], ev[3]));
-          fprintf(stderr, "[mps_b200 trace] layer %d B=%d sweep %d: %.3f ms, %d matrices still rotating\n", (int)nlayers, B, sweep, ms, *h_rem);
-          CK(cudaEventRecord(ev[5], stream));
-        }
-        if (*h_rem == 0) { ++sweep; break; }
-        rotating = std::min(B, std::max(1, *h_rem));
+        sweep = std::max(sweep, csweep);
+        ++nchunk;
+        (void)c1;
       }
-    } else
-    {
-      // contiguous slices of the (interleaved) batch per group
-      int goff[NGROUP + 1], gpairs[NGROUP], gsteps[NGROUP];
-      goff[0] = 0;
-      for (int g = 0; g < NG; ++g) {
-        const int cnt = (B - g + NG - 1) / NG;
-        goff[g + 1] = goff[g] + cnt;
-        gpairs[g] = 1; gsteps[g] = 1;
-        for (int b = goff[g]; b < goff[g + 1]; ++b) {
-          gpairs[g] = std::max(gpairs[g], hJ[b].nb == 1 ? 1 : hJ[b].nbe / 2);
-          gsteps[g] = std::max(gsteps[g], hJ[b].nb == 1 ? 1 : hJ[b].nbe - 1);
-        }
-      }
-      CK(cudaEventRecord(gstart, stream));
-      const JacobiProblem* dJ = (const JacobiProblem*)(wb + oJac);
-      int enq[NGROUP] = {}, seen[NGROUP] = {};
-      bool fin[NGROUP] = {};
-      auto enqueue = [&](int g) {
-        cudaStream_t gs = gstream[g];
-        const int o = goff[g], nb = goff[g + 1] - goff[g];
-        for (int st_ = 0; st_ < gsteps[g]; ++st_)
-          launch_jacobi_step(dJ + o, nb, gpairs[g], st_, tol2, dead2, d_fro2 + o, d_dirty + o, d_done + o, gs);
-        launch_jacobi_check(nb, d_dirty + o, d_done + o, d_rem + g, nullptr, gs);
-        nlaunch += gsteps[g] + 1;
-        const int slot = enq[g] % GDEPTH;
-        CK(cudaMemcpyAsync(pin_rem + g * GDEPTH + slot, d_rem + g, sizeof(int), cudaMemcpyDeviceToHost, gs));
-        CK(cudaEventRecord(gev[g][slot], gs));
-        ++enq[g];
-      };
-      for (int g = 0; g < NG; ++g) {
-        CK(cudaStreamWaitEvent(gstream[g], gstart, 0));
-        for (int d = 0; d < GDEPTH && d < max_sweeps; ++d) enqueue(g);
-      }
-      int active = NG;
-      while (active > 0) {
-        for (int g = 0; g < NG; ++g) {
-          if (fin[g]) continue;
-          const int slot = seen[g] % GDEPTH;
-          CK(cudaEventSynchronize(gev[g][slot]));
-          const int rem = pin_rem[g * GDEPTH + slot];
-          ++seen[g];
-          if (trace) fprintf(stderr, "[mps_b200 trace] layer %d B=%d group %d sweep %d: %d matrices still rotating\n", (int)nlayers, B, g, seen[g] - 1, rem);
-          if (rem == 0 || seen[g] >= max_sweeps) { fin[g] = true; --active; }
-          else if (enq[g] < max_sweeps) enqueue(g);
-        }
-      }
-      for (int g = 0; g < NG; ++g) {
-        sweep = std::max(sweep, seen[g]);
-        CK(cudaEventRecord(gend[g], gstream[g]));   // behind any speculative (no-op) sweep still queued
-        CK(cudaStreamWaitEvent(stream, gend[g], 0));
+      if (l2_persist && l2_window_max > 0) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.num_bytes = 0;   // window off for the write-back
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        CK(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
       }
     }
     nsweeps += sweep;
@@ -661,7 +648,7 @@ struct mps_b200_handle {
     launch_trunc((const TruncProblem*)(wb + oTr), B, cutoff, cutoff_on_sqrt, max_bond, gauge, renorm, ntol, stream);
     nlaunch += 1;
     const size_t keepBlkBytes = ((sizeof(int) * B + 15) & ~size_t(15)) + 2 * sizeof(double) * B;
-    char* rb = (char*)h_rem;
+    char* rb = (char*)h_rem + remBytes;
     CK(cudaMemcpyAsync(rb, wb + oKeepBlk, keepBlkBytes, cudaMemcpyDeviceToHost, stream));
     char* rbSig = rb + ((keepBlkBytes + 15) & ~size_t(15));
     CK(cudaMemcpyAsync(rbSig, wb + oSigmaBlk, sizeof(double) * sig_total, cudaMemcpyDeviceToHost, stream));
@@ -682,6 +669,25 @@ struct mps_b200_handle {
       const Dim& d = D[b];
       const int keep = h_keep[b];
       if (keep < 1 || keep > d.Ng) throw std::runtime_error("internal: bad kept bond dimension");
+      if (norm_guard) {
+        // post-SVD sanity check, ExaTnMpsVisitor.cpp:1632-1661: ||Q_lo||_2 and ||Q_hi||_2 of the un-truncated factors must
+        // both be >= 1e-3.  With the factors U f_lo(S) and f_hi(S) V^H these are sqrt(sum f(sigma_k)^2) -- known from the
+        // singular values alone, no pass over the sites.
+        double n_lo = 0.0, n_hi = 0.0;
+        for (int k = 0; k < d.Ng; ++k) {
+          const double s = h_sig[so + k];
+          if (!(s > 0.0)) continue;
+          n_lo += (gauge == 0) ? s : (gauge == 1 ? 1.0 : s * s);
+          n_hi += (gauge == 0) ? s : (gauge == 1 ? s * s : 1.0);
+        }
+        if (std::sqrt(n_lo) < 1e-3 || std::sqrt(n_hi) < 1e-3) {
+          guard_violations += 1;
+          if (norm_guard == 1)
+            throw std::runtime_error("tensor norm validation failed after the SVD on sites (" + std::to_string(d.lo) + "," + std::to_string(d.lo + 1) +
+                                     "): ||Q_lo|| = " + std::to_string(std::sqrt(n_lo)) + ", ||Q_hi|| = " + std::to_string(std::sqrt(n_hi)) +
+                                     " (ExaTnMpsVisitor.cpp:1632-1661; option norm_guard = 2 counts instead of failing)");
+        }
+      }
       if (h_w[2 * b] > 0) discarded += (h_w[2 * b] - h_w[2 * b + 1]) / h_w[2 * b];
       sv[d.lo].assign(h_sig + so, h_sig + so + keep);
       so += d.Ng;
@@ -1019,14 +1025,16 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
       CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
-    for (int g = 0; g < mps_b200_handle::NGROUP; ++g) {
-      CK(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
-      for (auto& ev : h->gev[g]) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&h->gend[g], cudaEventDisableTiming));
+    for (auto& ev : h->sev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    {
+      // persisting-L2 carve-out for the Jacobi work matrices (see run_layer); both limits are device properties
+      h->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
+      h->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
+      if (h->l2_persist_max > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max) != cudaSuccess) {
+        cudaGetLastError();
+        h->l2_persist_max = h->l2_window_max = 0;
+      }
     }
-    CK(cudaEventCreateWithFlags(&h->gstart, cudaEventDisableTiming));
-    for (auto& ev : h->qev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CK(cudaMallocHost(&h->pin_rem, sizeof(int) * mps_b200_handle::NGROUP * mps_b200_handle::GDEPTH));
     h->sites.resize(h->ntot);
     h->norm_ver.assign(h->nreg, 0);
     h->norm_val.assign(h->nreg, 0.0);
@@ -1036,19 +1044,14 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     h->sv.assign(std::max(h->ntot - 1, 1), std::vector<double>{1.0});
     // developer overrides for A/B runs of the whole test-suite
     if (const char* e = getenv("MPS_B200_QR")) h->use_qr = atoi(e) != 0;
-    if (const char* e = getenv("MPS_B200_GROUPS")) h->jacobi_groups = std::max(1, atoi(e));
-    if (const char* e = getenv("MPS_B200_PERSISTENT")) h->jacobi_persistent = atoi(e) != 0;
-    if (const char* e = getenv("MPS_B200_MAX_SWEEPS")) h->max_sweeps = std::max(1, atoi(e));
-    if (const char* e = getenv("MPS_B200_STAGGER_NS")) h->stagger_ns = atoi(e);
-    if (const char* e = getenv("MPS_B200_DISCARD_MARGIN")) h->discard_margin = atof(e);
+    if (const char* e = getenv("MPS_B200_MAX_SWEEPS")) h->max_sweeps = std::max(1, std::min(1000, atoi(e)));
     if (const char* e = getenv("MPS_B200_DBG_MODE")) jacobi_set_debug_mode(atoi(e));
     h->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("MPS_B200_JACOBI_TOL")) h->jacobi_tol = atof(e);
     if (const char* e = getenv("MPS_B200_NULL_TOL")) h->null_tol = atof(e);
-    if (const char* e = getenv("MPS_B200_3M")) { jacobi_set_3m(atoi(e)); h->jacobi_3m_on = atoi(e) != 0; }
     if (const char* e = getenv("MPS_B200_WIDE_TASKS")) h->wide_tasks = atoi(e) != 0;
-    if (const char* e = getenv("MPS_B200_QR_LOOKAHEAD")) h->qr_lookahead = atoi(e) != 0;
-    if (const char* e = getenv("MPS_B200_BLOCK16")) h->block16 = atoi(e) != 0;
+    if (const char* e = getenv("MPS_B200_CHUNK_MB")) h->chunk_mb = std::max(1, atoi(e));
+    if (const char* e = getenv("MPS_B200_L2_PERSIST")) h->l2_persist = atoi(e) != 0;
     if (const char* e = getenv("MPS_B200_CTAS_PER_SM")) h->ctas_per_sm = std::max(0, std::min(4, atoi(e)));
     if (const char* e = getenv("MPS_B200_SMALL_GEMM")) gemm_set_small_path(atoi(e));
     if (seed) h->rng.seed(seed);
@@ -1075,14 +1078,7 @@ int mps_destroy(mps_handle_t h) {
   for (int i = 0; i < 2; ++i) if (h->pin[i]) cudaFreeHost(h->pin[i]);
   if (h->pin_rb) cudaFreeHost(h->pin_rb);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
-  for (int g = 0; g < mps_b200_handle::NGROUP; ++g) {
-    if (h->gstream[g]) { cudaStreamSynchronize(h->gstream[g]); cudaStreamDestroy(h->gstream[g]); }
-    for (auto& ev : h->gev[g]) if (ev) cudaEventDestroy(ev);
-    if (h->gend[g]) cudaEventDestroy(h->gend[g]);
-  }
-  if (h->gstart) cudaEventDestroy(h->gstart);
-  for (auto& ev : h->qev) if (ev) cudaEventDestroy(ev);
-  if (h->pin_rem) cudaFreeHost(h->pin_rem);
+  for (auto& ev : h->sev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -1097,27 +1093,25 @@ int mps_restore(mps_handle_t h) { API_BEGIN(h) h->restore_state(); API_END(h) }
 int mps_set_option(mps_handle_t h, const char* key, double value) {
   API_BEGIN(h)
   std::string k(key);
-  if (k == "cutoff_on_sqrt") h->cutoff_on_sqrt = value != 0;
+  // options that change how queued gates would be executed flush the queue first
+  if (k == "cutoff_on_sqrt") { h->flush(); h->cutoff_on_sqrt = value != 0; }
   else if (k == "fuse_1q") { h->flush(); h->fuse_1q = value != 0; }
   else if (k == "fuse_2q") { h->flush(); h->fuse_2q = value != 0; }
-  else if (k == "renormalize") h->renorm = value != 0;
-  else if (k == "jacobi_tol") h->jacobi_tol = value;
-  else if (k == "null_tol") h->null_tol = value;
-  else if (k == "jacobi_max_sweeps") h->max_sweeps = (int)value;
+  else if (k == "renormalize") { h->flush(); h->renorm = value != 0; }
+  else if (k == "jacobi_tol") { h->flush(); h->jacobi_tol = value; }
+  else if (k == "null_tol") { h->flush(); h->null_tol = value; }
+  else if (k == "jacobi_max_sweeps") { h->flush(); h->max_sweeps = std::max(1, std::min(1000, (int)value)); }
   else if (k == "profile") h->profile = value != 0;
   else if (k == "layer_batch") { h->flush(); h->layer_batch = value != 0; }
   else if (k == "qr_prereduce") { h->flush(); h->use_qr = value != 0; }
-  else if (k == "jacobi_groups") { h->flush(); h->jacobi_groups = std::max(1, (int)value); }
-  else if (k == "jacobi_persistent") { h->flush(); h->jacobi_persistent = value != 0; }
-  else if (k == "discard_margin") { h->flush(); h->discard_margin = value; }
-  else if (k == "jacobi_3m") { h->flush(); jacobi_set_3m(value != 0); h->jacobi_3m_on = value != 0; }
   else if (k == "jacobi_wide_tasks") { h->flush(); h->wide_tasks = value != 0; }
-  else if (k == "qr_lookahead") { h->flush(); h->qr_lookahead = value != 0; }
-  else if (k == "jacobi_block16") { h->flush(); h->block16 = value != 0; }
   else if (k == "jacobi_ctas_per_sm") { h->flush(); h->ctas_per_sm = std::max(0, std::min(4, (int)value)); }
-  else if (k == "max_bond") h->max_bond = value > 0 ? (int)value : INT_MAX - 1;
-  else if (k == "svd_cutoff") h->cutoff = value >= 0 ? value : DBL_MIN;
-  else if (k == "gauge") h->gauge = (int)value;
+  else if (k == "jacobi_chunk_mb") { h->flush(); h->chunk_mb = std::max(1, (int)value); }
+  else if (k == "l2_persist") { h->flush(); h->l2_persist = value != 0; }
+  else if (k == "norm_guard") { h->flush(); h->norm_guard = std::max(0, std::min(2, (int)value)); }
+  else if (k == "max_bond") { h->flush(); h->max_bond = value > 0 ? (int)value : INT_MAX - 1; }
+  else if (k == "svd_cutoff") { h->flush(); h->cutoff = value >= 0 ? value : DBL_MIN; }
+  else if (k == "gauge") { h->flush(); if (value < 0 || value > 2) throw std::runtime_error("unknown gauge"); h->gauge = (int)value; }
   else throw std::runtime_error("unknown option: " + k);
   API_END(h)
 }
@@ -1343,8 +1337,9 @@ int mps_stats(mps_handle_t h, double* out, int cap) {
   API_BEGIN(h)
   h->flush();
   CK(cudaStreamSynchronize(h->stream));
-  const double v[11] = {h->n2q, h->n1q, h->nlayers, h->nsweeps, h->nlaunch, h->ms_theta, h->ms_svd, h->ms_wb, h->ms_qr, jacobi_dmma_flops(), h->nfused2q};
-  for (int i = 0; i < cap && i < 11; ++i) out[i] = v[i];
+  const double v[13] = {h->n2q, h->n1q, h->nlayers, h->nsweeps, h->nlaunch, h->ms_theta, h->ms_svd, h->ms_wb, h->ms_qr, jacobi_dmma_flops(), h->nfused2q,
+                        h->nonconverged, h->guard_violations};
+  for (int i = 0; i < cap && i < 13; ++i) out[i] = v[i];
   API_END(h)
 }
 

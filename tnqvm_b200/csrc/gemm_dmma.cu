@@ -202,6 +202,9 @@ __device__ __forceinline__ void zgemm_dmma_body(const GemmProblem* __restrict__ 
               }
               const int row = a + M * (o >> 1), col = (o & 1) + 2 * c;
               const size_t idx = cT ? ((size_t)col + (size_t)ldc * row) : ((size_t)row + (size_t)ldc * col);
+              // stabilizeTensorBody (ExaTnMpsVisitor.cpp:141-161): elements of the merged tensor with |x| < 1e-100 are
+              // set to zero before the SVD
+              if (re * re + im * im < 1e-200) { re = 0.0; im = 0.0; }
               const double2 v = make_double2(re, cT ? -im : im);
               C[idx] = v;
               if (C2) C2[idx] = v;

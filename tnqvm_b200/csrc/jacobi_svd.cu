@@ -57,7 +57,16 @@ __device__ __forceinline__ bool pair_blocks(const JacobiProblem& P, int step, in
 // columns were last written by a CTA on another SM.
 // NWARP = warps per task: 4 when the SMs hold several tasks each, 8 when a tournament step has fewer tasks than SMs (layers
 // of one to four gates in routed circuits) and the latency of the two streaming phases of a lone task is what counts.
-template <bool M3, int NWARP>
+//
+// Phase C applies the rotations of phase B to the rows of X directly (one thread per row, the 16 entries of the row in
+// registers) instead of accumulating a dense 16x16 Q and multiplying by it: on B200 the FP64 tensor pipe has the same
+// FMA rate as the scalar FP64 pipe (both ~37 TFLOP/s), so what counts is the FMA count, and 64 plane rotations in their
+// scaled ("fast Givens") form cost 64 x 8 + 32 = 544 FMA per row against 1024 for the dense complex 16x16 product.
+// Every column carries a real scale gamma (product of the cosines it has been through in this task): with x = gamma x',
+//   x'_p <- x'_p - tp x'_q,  x'_q <- x'_q + tq x'_p(old),   tp = conj(s/c) gamma_q / gamma_p,  tq = (s/c) gamma_p / gamma_q,
+// and x = gamma x' once at the end.  gamma stays within [2^-7.5, 1] (|angle| <= pi/4, at most 15 rotations per column).
+constexpr int MAXROT = 120;   // 8 cross rounds (+ 7 in-block rounds at the first step of a tournament) x 8 rotations
+template <int NWARP>
 __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int blkA, int blkB, bool within, double tol2, double dead2,
                                           const double* __restrict__ fro2, int* __restrict__ dirty) {
   const int M = P.M, N = P.N, ldg = P.ldg;
@@ -65,13 +74,13 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   // columns whose squared norm is below dead_abs (<= (null_tol * sigma_max)^2) are numerically null: they are zeroed at
   // write-back and never rotated, so rank-deficient thetas do not spend sweeps orthogonalising rounding noise
   const double dead_abs = dead2 * fro2[mat] / (double)N;
-  const double thr = *P.thr;   // both columns below thr: both will be truncated, leave the pair alone
 
   __shared__ int s_cols[16];
   constexpr int NT = 32 * NWARP;
   __shared__ double s_red[NWARP][7][64];
   __shared__ double2 sW[16 * WLD];
-  __shared__ double2 sQ[16 * WLD];
+  __shared__ double2 s_tp[MAXROT], s_tq[MAXROT];   // scaled rotation parameters in application order
+  __shared__ double s_gam[16], s_igam[16];
   __shared__ double s_rc[8];
   __shared__ double2 s_rs[8];
   __shared__ int s_rp[8], s_rq[8];
@@ -83,19 +92,10 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     if (tid < 8) c = blkA * 8 + tid;
     else c = (blkB >= 0) ? blkB * 8 + (tid - 8) : N;
     s_cols[tid] = (c < N) ? c : -1;
+    s_gam[tid] = 1.0; s_igam[tid] = 1.0;
   }
   if (tid == 0) s_need = 0;
   __syncthreads();
-  if (thr > 0.0) {
-    // all 16 columns already below the threshold: nothing this task could rotate, skip even the Gram matrix
-    if (tid < 16 && s_cols[tid] >= 0 && __ldcg(P.cn2 + s_cols[tid]) >= thr) s_need = 1;
-    __syncthreads();
-    const int any = s_need;
-    __syncthreads();
-    if (!any) return;
-    if (tid == 0) s_need = 0;
-    __syncthreads();
-  }
   if (!within && blkB < 0) return;   // a lone block has no cross pairs
   // Clean-pair memo: ver[b] counts the rotations block b has been through; rec[A][B] remembers the two versions at which the
   // cross pairs of (A, B) were last found orthogonal.  If neither block has changed since, the task is over before it loads
@@ -199,7 +199,6 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     else if (bp == 0) { re = s_red[0][4][r * 8 + c]; im = s_red[0][5][r * 8 + c] - s_red[0][6][r * 8 + c]; }
     else { re = s_red[0][4][c * 8 + r]; im = -(s_red[0][5][c * 8 + r] - s_red[0][6][c * 8 + r]); }
     sW[p * WLD + q] = make_double2(re, im);
-    sQ[p * WLD + q] = make_double2(p == q ? 1.0 : 0.0, 0.0);
   }
   __syncthreads();
   // fresh-Gram convergence test over the pairs this task is responsible for
@@ -210,7 +209,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
       if (p < q && (within || (p < 8 && q >= 8))) {   // pairs inside a block belong to the first step of the tournament
         const double a = sW[p * WLD + p].x, b = sW[q * WLD + q].x;
         const double2 g = sW[p * WLD + q];
-        if (a > dead_abs && b > dead_abs && (a >= thr || b >= thr) && (g.x * g.x + g.y * g.y) > tol2 * a * b) need = 1;
+        if (a > dead_abs && b > dead_abs && (g.x * g.x + g.y * g.y) > tol2 * a * b) need = 1;
       }
     }
     if (need) s_need = 1;   // benign race: all writers store 1
@@ -218,7 +217,6 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   __syncthreads();
   if (timing) { tC = clock64(); atomicAdd(&g_phase_cycles[0], (unsigned long long)(tB - tA)); atomicAdd(&g_phase_cycles[1], (unsigned long long)(tC - tB)); atomicAdd(&g_phase_cycles[5], 1ull); }
   if (!s_need) {
-    if (tid < 16 && s_cols[tid] >= 0) P.cn2[s_cols[tid]] = sW[tid * WLD + tid].x;
     if (!within && tid == 0) {
       const int va = blkA < blkB ? verA : verB, vb = blkA < blkB ? verB : verA;
       *recp = make_int2(va + 1, vb + 1);
@@ -230,16 +228,16 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     if (tid == 0) atomicAdd(&g_dmma_flops, (unsigned long long)((M + 3) >> 2) * (within ? 5120ull : 2048ull));   // Gram: 10 (4) DMMA per 4 rows
     return;
   }
-  if (tid == 0) atomicAdd(&g_dmma_flops, (unsigned long long)((M + 3) >> 2) * (within ? 5120ull : 2048ull) + (unsigned long long)((M + 7) >> 3) * (M3 ? 12288ull : 16384ull));
+  const int nrounds = within ? 15 : 8;
+  if (tid == 0) atomicAdd(&g_dmma_flops, (unsigned long long)((M + 3) >> 2) * (within ? 5120ull : 2048ull) + (unsigned long long)M * (unsigned long long)(2 * (nrounds * 64 + 32)));
   if (tid == 0) dirty[mat] = 1;
 
-  // ------------------------------------------------------------------ phase B: Jacobi rotations on W (warps 0-3; warps 4-7 of an 8-warp task only take the barriers)
+  // ------------------------------------------------------------------ phase B: Jacobi rotations on W (warps 0-1; the other warps only take the barriers)
   // Round r rotates 8 disjoint column pairs.  Rounds 0-7 are the bipartite schedule over the cross pairs (i, 8 + (i+r)%8);
   // rounds 8-14 (only when `within`: the first step of a tournament) are the two 8-column round-robins of the pairs
   // inside each block, which every later step of the sweep leaves alone.  Lanes 0-7 of warp 0 compute the rotations
-  // (two rsqrt, no division or sqrt), warps 0-1 apply them to W two-sidedly, warps 2-3 accumulate Q.
+  // (two rsqrt, no division or sqrt) and their scaled form for phase C, warps 0-1 apply them to W two-sidedly.
   {
-    const int nrounds = within ? 15 : 8;
     for (int r = 0; r < nrounds; ++r) {
       int rot = 0;
       if (tid < 8) {
@@ -257,17 +255,26 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
         const double g2 = g.x * g.x + g.y * g.y;
         double c = 1.0;
         double2 sg = make_double2(0.0, 0.0);
-        if (a > dead_abs && b > dead_abs && (a >= thr || b >= thr) && g2 > tol2 * a * b) {
+        double2 tp = make_double2(0.0, 0.0), tq = make_double2(0.0, 0.0);
+        if (a > dead_abs && b > dead_abs && g2 > tol2 * a * b) {
           rot = 1;
           // cos 2t = |d|/h, sin 2t = 2|g|/h  (|t| <= pi/4):  c = sqrt((1 + |d|/h)/2),  s = sign(d) g / (h c)
           const double d = b - a;
           const double rh = rsqrt(d * d + 4.0 * g2);
           const double x = 0.5 * (1.0 + fabs(d) * rh);
-          const double rx = rsqrt(x);
+          const double rx = rsqrt(x);   // 1 / c
           c = x * rx;
           sg = rmul(d >= 0.0 ? rh * rx : -(rh * rx), g);
+          // scaled form: t = s / c; the columns carry gamma_p, gamma_q
+          const double2 t = rmul(rx, sg);
+          const double gp = s_gam[p], gq = s_gam[q], igp = s_igam[p], igq = s_igam[q];
+          tp = rmul(gq * igp, make_double2(t.x, -t.y));
+          tq = rmul(gp * igq, t);
+          s_gam[p] = gp * c; s_gam[q] = gq * c;
+          s_igam[p] = igp * rx; s_igam[q] = igq * rx;
         }
         s_rc[tid] = c; s_rs[tid] = sg; s_rp[tid] = p; s_rq[tid] = q;
+        s_tp[r * 8 + tid] = tp; s_tq[r * 8 + tid] = tq;
       }
       if (!__syncthreads_or(rot)) continue;
       if (warp < 2) {
@@ -286,24 +293,10 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
         sW[pa * WLD + qb] = cadd(cmul(sb, t00), rmul(cb, t01));
         sW[qa * WLD + pb] = csub(rmul(cb, t10), cmulc(sb, t11));
         sW[qa * WLD + qb] = cadd(cmul(sb, t10), rmul(cb, t11));
-      } else if (warp < 4) {
-        // Q <- Q J
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int it = (tid - 64) + 64 * k;
-          const int row = it >> 3, ia = it & 7;
-          const int pa = s_rp[ia], qa = s_rq[ia];
-          const double ca = s_rc[ia];
-          const double2 sa = s_rs[ia];
-          const double2 x = sQ[row * WLD + pa], y = sQ[row * WLD + qa];
-          sQ[row * WLD + pa] = csub(rmul(ca, x), cmulc(sa, y));
-          sQ[row * WLD + qa] = cadd(cmul(sa, x), rmul(ca, y));
-        }
       }
       __syncthreads();
     }
   }
-  if (tid < 16 && s_cols[tid] >= 0) P.cn2[s_cols[tid]] = sW[tid * WLD + tid].x;   // the last round ended with a barrier
   if (tid == 0) {   // this task is the only owner of both blocks during this step
     if (within) { verA = __ldcg(P.ver + blkA); if (blkB >= 0) verB = __ldcg(P.ver + blkB); }
     P.ver[blkA] = verA + 1;
@@ -316,108 +309,66 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   __syncthreads();
   if (timing) { tD = clock64(); atomicAdd(&g_phase_cycles[2], (unsigned long long)(tD - tC)); }
 
-  // ------------------------------------------------------------------ phase C: X <- X Q on DMMA, in place
+  // ------------------------------------------------------------------ phase C: the rotations applied to the rows of X, in place
   {
-    double2 qf[4][2];
+    // the two blocks are 8 consecutive columns each; nA / nB of them exist (N need not be a multiple of 8)
+    double2* const baseA = G + (size_t)ldg * (blkA * 8);
+    double2* const baseB = (blkB >= 0) ? G + (size_t)ldg * (blkB * 8) : G;
+    const int nA = min(8, N - blkA * 8), nB = (blkB >= 0) ? min(8, N - blkB * 8) : 0;
+    for (int row = tid; row < M; row += NT) {
+      double2 x[16];
+      {
+        const double2* pa = baseA + row;
+        const double2* pb = baseB + row;
 #pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4)
-#pragma unroll
-      for (int jn = 0; jn < 2; ++jn) qf[k4][jn] = sQ[(4 * k4 + (lane & 3)) * WLD + 8 * jn + (lane >> 2)];
-    double qs[4][2];
-#pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4)
-#pragma unroll
-      for (int jn = 0; jn < 2; ++jn) qs[k4][jn] = qf[k4][jn].x + qf[k4][jn].y;
-    const double2* src[4];
-#pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4) {
-      const int c = s_cols[4 * k4 + (lane & 3)];
-      src[k4] = (c >= 0) ? G + (size_t)ldg * c : nullptr;
-    }
-    double2* dst[2][2];
-#pragma unroll
-    for (int jn = 0; jn < 2; ++jn)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = s_cols[8 * jn + 2 * (lane & 3) + e];
-        dst[jn][e] = (c >= 0) ? G + (size_t)ldg * c : nullptr;
-      }
-    const int nch = (M + 7) >> 3;
-    constexpr int UN = 2;
-    for (int base = warp * UN; base < nch; base += NWARP * UN) {
-      double2 xa[UN][4];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int row = 8 * (base + u) + (lane >> 2);
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) xa[u][k4] = (row < M && src[k4]) ? __ldcg(src[k4] + row) : make_double2(0.0, 0.0);
+        for (int j = 0; j < 8; ++j) {
+          x[j] = (j < nA) ? __ldcg(pa) : make_double2(0.0, 0.0);
+          x[8 + j] = (j < nB) ? __ldcg(pb) : make_double2(0.0, 0.0);
+          pa += ldg; pb += ldg;
+        }
       }
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        double re[2][2] = {{0, 0}, {0, 0}}, im[2][2] = {{0, 0}, {0, 0}};
-        if (M3) {
-          // 3M complex product: T1 = Xr Qr, T2 = Xi Qi, T3 = (Xr + Xi)(Qr + Qi);  Re = T1 - T2, Im = T3 - T1 - T2
-          // (24 instead of 32 DMMA per 8 rows; the error stays of order eps |X| |Q| per term)
-          double t2[2][2] = {{0, 0}, {0, 0}};
+      for (int r = 0; r < 8; ++r) {
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const double ar = xa[u][k4].x, ai = xa[u][k4].y, as = ar + ai;
+        for (int i = 0; i < 8; ++i) {
+          const int p = i, q = 8 + ((i + r) & 7);
+          const double2 tp = s_tp[r * 8 + i], tq = s_tq[r * 8 + i];
+          const double2 xp = x[p], xq = x[q];
+          x[p] = make_double2(fma(-tp.x, xq.x, fma(tp.y, xq.y, xp.x)), fma(-tp.x, xq.y, fma(-tp.y, xq.x, xp.y)));
+          x[q] = make_double2(fma(tq.x, xp.x, fma(-tq.y, xp.y, xq.x)), fma(tq.x, xp.y, fma(tq.y, xp.x, xq.y)));
+        }
+      }
+      if (within) {
 #pragma unroll
-            for (int jn = 0; jn < 2; ++jn) {
-              dmma884(re[jn][0], re[jn][1], ar, qf[k4][jn].x);
-              dmma884(t2[jn][0], t2[jn][1], ai, qf[k4][jn].y);
-              dmma884(im[jn][0], im[jn][1], as, qs[k4][jn]);
-            }
-          }
+        for (int w = 0; w < 7; ++w) {
 #pragma unroll
-          for (int jn = 0; jn < 2; ++jn)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const double t1 = re[jn][e];
-              re[jn][e] = t1 - t2[jn][e];
-              im[jn][e] = im[jn][e] - t1 - t2[jn][e];
-            }
-        } else {
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const double ar = xa[u][k4].x, ai = xa[u][k4].y, nai = -ai;
-#pragma unroll
-          for (int jn = 0; jn < 2; ++jn) {
-            dmma884(re[jn][0], re[jn][1], ar, qf[k4][jn].x);
-            dmma884(im[jn][0], im[jn][1], ar, qf[k4][jn].y);
-            dmma884(re[jn][0], re[jn][1], nai, qf[k4][jn].y);
-            dmma884(im[jn][0], im[jn][1], ai, qf[k4][jn].x);
+          for (int i = 0; i < 8; ++i) {
+            const int l = i & 3, off = (i >> 2) * 8;
+            int p = (l == 0) ? 7 : (w + l) % 7;
+            int q = (w + 7 - l) % 7;
+            if (p > q) { const int t = p; p = q; q = t; }
+            p += off; q += off;
+            const double2 tp = s_tp[(8 + w) * 8 + i], tq = s_tq[(8 + w) * 8 + i];
+            const double2 xp = x[p], xq = x[q];
+            x[p] = make_double2(fma(-tp.x, xq.x, fma(tp.y, xq.y, xp.x)), fma(-tp.x, xq.y, fma(-tp.y, xq.x, xp.y)));
+            x[q] = make_double2(fma(tq.x, xp.x, fma(-tq.y, xp.y, xq.x)), fma(tq.x, xp.y, fma(tq.y, xp.x, xq.y)));
           }
         }
-        }
-        const int row = 8 * (base + u) + (lane >> 2);
-        if (row < M) {
+      }
+      {
+        double2* pa = baseA + row;
+        double2* pb = baseB + row;
 #pragma unroll
-          for (int jn = 0; jn < 2; ++jn)
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-              if (dst[jn][e]) dst[jn][e][row] = make_double2(re[jn][e], im[jn][e]);
+        for (int j = 0; j < 8; ++j) {
+          const double ga = s_gam[j], gb = s_gam[8 + j];
+          if (j < nA) *pa = make_double2(ga * x[j].x, ga * x[j].y);
+          if (j < nB) *pb = make_double2(gb * x[8 + j].x, gb * x[8 + j].y);
+          pa += ldg; pb += ldg;
         }
       }
     }
   }
   if (timing) { atomicAdd(&g_phase_cycles[3], (unsigned long long)(clock64() - tD)); atomicAdd(&g_phase_cycles[6], 1ull); }
-}
-
-// One step of the tournament for the whole batch (grid = pairs x matrices); kept for A/B runs (option "jacobi_persistent" 0).
-template <bool M3>
-__global__ void __launch_bounds__(JT, 4) jacobi_step_kernel(const JacobiProblem* __restrict__ probs, int step, double tol2, double dead2,
-                                                            const double* __restrict__ fro2, int* __restrict__ dirty,
-                                                            const int* __restrict__ done) {
-  const int mat = blockIdx.y;
-  if (done[mat]) return;
-  const JacobiProblem P = probs[mat];
-  const int npairs = (P.nb == 1) ? 1 : P.nbe / 2;
-  if ((int)blockIdx.x >= npairs) return;
-  int blkA, blkB;
-  bool within;
-  if (!pair_blocks(P, step, blockIdx.x, blkA, blkB, within)) return;
-  pair_task<M3, 4>(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
 }
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -433,12 +384,12 @@ __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.rel
 // Tasks are dequeued in dependency order and a waiting CTA only waits on tasks dequeued before its own, which are
 // finished or running on resident CTAs, so the scheme cannot deadlock.  Compared with one launch per step this removes
 // ~60 launch boundaries per sweep and lets the Gram / rotate / apply phases of different pairs overlap on an SM.
-template <bool M3, int NWARP>
+template <int NWARP>
 __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) jacobi_sweep_kernel(const JacobiProblem* __restrict__ probs, int batch, int max_pairs, int nsteps,
                                                              int base, double tol2, double dead2, const double* __restrict__ fro2,
                                                              int* __restrict__ dirty, const int* __restrict__ done,
                                                              int* __restrict__ progress, int progress_stride, int* __restrict__ counter,
-                                                             int* __restrict__ fault, int stagger_ns, const int* __restrict__ active) {
+                                                             int* __restrict__ fault, const int* __restrict__ active) {
   __shared__ int s_task;
   // active (optional): [0] = number of matrices still rotating, [1..] their indices (written by jacobi_check_kernel)
   if (active) batch = __ldcg(active);
@@ -464,12 +415,6 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) jacobi_sweep_kernel(co
     long long tw = 0;
     if (threadIdx.x == 0 && g_dbg_mode == 10) tw = clock64();
     if (threadIdx.x == 0) {
-      // Every block of a matrix takes part in every step, so the tasks of one matrix move in lockstep and the DMMA pipe
-      // idles while they are all in the serial rotation phase.  Delaying every other matrix by part of a step at the
-      // start of the sweep puts the matrices out of phase with each other.
-      if (step == 0 && (mat & 1) && stagger_ns > 0) {
-        for (int w = 0; w < stagger_ns; w += 1000) __nanosleep(1000);
-      }
       // bounded wait (~1 s): a scheduling bug must surface as an error on the host, never as a hung GPU
       const int need = base + step;
       unsigned spins = 0;
@@ -480,7 +425,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) jacobi_sweep_kernel(co
     }
     __syncthreads();
     if (threadIdx.x == 0 && g_dbg_mode == 10) atomicAdd(&g_phase_cycles[4], (unsigned long long)(clock64() - tw));
-    pair_task<M3, NWARP>(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
+    pair_task<NWARP>(P, mat, blkA, blkB, within || g_dbg_mode == 4, tol2, dead2, fro2, dirty);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -490,410 +435,6 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) jacobi_sweep_kernel(co
   }
 }
 
-// =====================================================================================================================
-// 16-column blocks (a task owns 32 columns): per sweep the columns make 31 passes through L2 instead of 63, which is what
-// the streaming phases are bound by; the price is a 32x32 rotation problem per task (16 rounds of 16 rotations).
-// Same structure as pair_task: cross Gram on DMMA (the 16x16 Gram blocks of the two column blocks travel with them),
-// rotations in shared memory, X <- X Q on DMMA; the discard rule and 3M product are not offered here.
-constexpr int W32 = 33;   // leading dimension of the 32x32 shared matrices
-constexpr int JT16 = 256;  // threads per task: only ~1.8 tasks per SM exist at a time, so a task needs many warps to stream its columns
-constexpr int NW16 = JT16 / 32;
-struct Smem16 {
-  double red[NW16][12][64];      // per-warp Gram fragments (cross: 4 block pairs x (re, p, q); 16-column Gram: 7 planes)
-  double2 W[32 * W32];
-  double2 Q[32 * W32];
-  double rc[16];
-  double2 rs[16];
-  int rp[16], rq[16];
-  int cols[32];
-  int need;
-};
-
-// Hermitian Gram of 16 columns (cols[0..15]) into W[off + r][off + c], all four warps; ends with a barrier
-__device__ __forceinline__ void gram16_diag(Smem16& S, const double2* G, int ldg, int M, const int* cols, int off, int tid) {
-  const int warp = tid >> 5, lane = tid & 31;
-  const int slot = lane >> 2, rsub = lane & 3;
-  const int c0 = cols[slot], c1 = cols[8 + slot];
-  const double2* p0 = (c0 >= 0) ? G + (size_t)ldg * c0 : nullptr;
-  const double2* p1 = (c1 >= 0) ? G + (size_t)ldg * c1 : nullptr;
-  double w00[2] = {0, 0}, m00[2] = {0, 0}, w11[2] = {0, 0}, m11[2] = {0, 0}, w01[2] = {0, 0}, p01[2] = {0, 0}, q01[2] = {0, 0};
-  const int nch = (M + 3) >> 2;
-  constexpr int UN = 4;
-  for (int base = warp * UN; base < nch; base += NW16 * UN) {
-    double2 x0[UN], x1[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int row = 4 * (base + u) + rsub;
-      const bool ok = row < M;
-      x0[u] = (ok && p0) ? __ldcg(p0 + row) : make_double2(0.0, 0.0);
-      x1[u] = (ok && p1) ? __ldcg(p1 + row) : make_double2(0.0, 0.0);
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      dmma884(w00[0], w00[1], x0[u].x, x0[u].x);
-      dmma884(m00[0], m00[1], x0[u].x, x0[u].y);
-      dmma884(w11[0], w11[1], x1[u].x, x1[u].x);
-      dmma884(m11[0], m11[1], x1[u].x, x1[u].y);
-      dmma884(w01[0], w01[1], x0[u].x, x1[u].x);
-      dmma884(p01[0], p01[1], x0[u].x, x1[u].y);
-      dmma884(q01[0], q01[1], x0[u].y, x1[u].x);
-      dmma884(w00[0], w00[1], x0[u].y, x0[u].y);
-      dmma884(w11[0], w11[1], x1[u].y, x1[u].y);
-      dmma884(w01[0], w01[1], x0[u].y, x1[u].y);
-    }
-  }
-  const int e0 = (lane >> 2) * 8 + 2 * (lane & 3);
-  S.red[warp][0][e0] = w00[0]; S.red[warp][0][e0 + 1] = w00[1];
-  S.red[warp][1][e0] = m00[0]; S.red[warp][1][e0 + 1] = m00[1];
-  S.red[warp][2][e0] = w11[0]; S.red[warp][2][e0 + 1] = w11[1];
-  S.red[warp][3][e0] = m11[0]; S.red[warp][3][e0 + 1] = m11[1];
-  S.red[warp][4][e0] = w01[0]; S.red[warp][4][e0 + 1] = w01[1];
-  S.red[warp][5][e0] = p01[0]; S.red[warp][5][e0 + 1] = p01[1];
-  S.red[warp][6][e0] = q01[0]; S.red[warp][6][e0 + 1] = q01[1];
-  __syncthreads();
-  for (int i = tid; i < 7 * 64; i += JT16) {
-    const int t = i >> 6, e = i & 63;
-    double acc = S.red[0][t][e];
-#pragma unroll
-    for (int w = 1; w < NW16; ++w) acc += S.red[w][t][e];
-    S.red[0][t][e] = acc;
-  }
-  __syncthreads();
-  for (int i = tid; i < 256; i += JT16) {
-    const int p = i >> 4, q = i & 15;
-    const int bp = p >> 3, bq = q >> 3, r = p & 7, c = q & 7;
-    double re, im;
-    if (bp == 0 && bq == 0) { re = S.red[0][0][r * 8 + c]; im = S.red[0][1][r * 8 + c] - S.red[0][1][c * 8 + r]; }
-    else if (bp == 1 && bq == 1) { re = S.red[0][2][r * 8 + c]; im = S.red[0][3][r * 8 + c] - S.red[0][3][c * 8 + r]; }
-    else if (bp == 0) { re = S.red[0][4][r * 8 + c]; im = S.red[0][5][r * 8 + c] - S.red[0][6][r * 8 + c]; }
-    else { re = S.red[0][4][c * 8 + r]; im = -(S.red[0][5][c * 8 + r] - S.red[0][6][c * 8 + r]); }
-    S.W[(off + p) * W32 + off + q] = make_double2(re, im);
-  }
-  __syncthreads();
-}
-
-// the i-th pair (p < q) of rotation round r on 32 columns: rounds 0-15 cross pairs, rounds 16-30 the two in-block round-robins
-__device__ __forceinline__ void jacobi_pair32(int r, int i, int& p, int& q) {
-  if (r < 16) { p = i; q = 16 + ((i + r) & 15); }
-  else {
-    const int w = r - 16, l = i & 7, off = (i >> 3) * 16;
-    p = (l == 0) ? 15 : (w + l) % 15;
-    q = (w + 15 - l) % 15;
-    if (p > q) { const int t = p; p = q; q = t; }
-    p += off; q += off;
-  }
-}
-
-__device__ __forceinline__ void pair_task16(Smem16& S, const JacobiProblem& P, int mat, int blkA, int blkB, bool within, double tol2,
-                                            double dead2, const double* __restrict__ fro2, int* __restrict__ dirty) {
-  const int M = P.M, N = P.N, ldg = P.ldg;
-  double2* G = P.G;
-  const double dead_abs = dead2 * fro2[mat] / (double)N;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (!within && blkB < 0) return;   // a lone block has no cross pairs
-  if (tid < 32) {
-    int c;
-    if (tid < 16) c = blkA * 16 + tid;
-    else c = (blkB >= 0) ? blkB * 16 + (tid - 16) : N;
-    S.cols[tid] = (c < N) ? c : -1;
-  }
-  if (tid == 0) S.need = 0;
-  // clean-pair memo (see pair_task)
-  int verA = 0, verB = 0;
-  int2* recp = nullptr;
-  if (!within) {
-    verA = __ldcg(P.ver + blkA); verB = __ldcg(P.ver + blkB);
-    recp = P.rec + (size_t)min(blkA, blkB) * P.nbe + max(blkA, blkB);
-    const int2 rec = __ldcg(recp);
-    const int va = blkA < blkB ? verA : verB, vb = blkA < blkB ? verB : verA;
-    if (rec.x == va + 1 && rec.y == vb + 1) return;
-  }
-  __syncthreads();
-  const bool timing = (g_dbg_mode == 10) && tid == 0;
-  long long tA = 0, tC = 0, tD = 0;
-  if (timing) tA = clock64();
-
-  // ------------------------------------------------------------------ phase A: cross Gram W_AB (16x16) on DMMA
-  if (blkB >= 0) {
-    const int slot = lane >> 2, rsub = lane & 3;
-    const double2* pc[4];
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const int c = S.cols[8 * h + slot];
-      pc[h] = (c >= 0) ? G + (size_t)ldg * c : nullptr;
-    }
-    double wr[2][2][2], wp[2][2][2], wq[2][2][2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) { wr[i][j][0] = wr[i][j][1] = wp[i][j][0] = wp[i][j][1] = wq[i][j][0] = wq[i][j][1] = 0.0; }
-    const int nch = (M + 3) >> 2;
-    constexpr int UN = 2;
-    for (int base = warp * UN; base < nch; base += NW16 * UN) {
-      double2 x[UN][4];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int row = 4 * (base + u) + rsub;
-        const bool ok = row < M;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) x[u][h] = (ok && pc[h]) ? __ldcg(pc[h] + row) : make_double2(0.0, 0.0);
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u)
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const double2 a = x[u][i], b = x[u][2 + j];
-            dmma884(wr[i][j][0], wr[i][j][1], a.x, b.x);
-            dmma884(wp[i][j][0], wp[i][j][1], a.x, b.y);
-            dmma884(wq[i][j][0], wq[i][j][1], a.y, b.x);
-            dmma884(wr[i][j][0], wr[i][j][1], a.y, b.y);
-          }
-    }
-    const int e0 = (lane >> 2) * 8 + 2 * (lane & 3);
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int pl = 3 * (2 * i + j);
-        S.red[warp][pl][e0] = wr[i][j][0]; S.red[warp][pl][e0 + 1] = wr[i][j][1];
-        S.red[warp][pl + 1][e0] = wp[i][j][0]; S.red[warp][pl + 1][e0 + 1] = wp[i][j][1];
-        S.red[warp][pl + 2][e0] = wq[i][j][0]; S.red[warp][pl + 2][e0 + 1] = wq[i][j][1];
-      }
-  }
-  __syncthreads();
-  for (int i = tid; i < 12 * 64; i += JT16) {
-    const int t = i >> 6, e = i & 63;
-    double acc = S.red[0][t][e];
-#pragma unroll
-    for (int w = 1; w < NW16; ++w) acc += S.red[w][t][e];
-    S.red[0][t][e] = acc;
-  }
-  __syncthreads();
-  // W = [W_AA W_AB; W_AB^H W_BB], Q = I.  Cross entries from the reduction (zero when there is no block B).
-  {
-    const double2* wdA = P.wd + (size_t)blkA * 256;
-    const double2* wdB = P.wd + (size_t)(blkB >= 0 ? blkB : blkA) * 256;
-    for (int i = tid; i < 1024; i += JT16) {
-      const int p = i >> 5, q = i & 31;
-      const int hp = p >> 4, hq = q >> 4;
-      double2 v = make_double2(0.0, 0.0);
-      if (hp != hq) {
-        if (blkB >= 0) {
-          const int a = hp ? q : p, b = (hp ? p : q) - 16;            // W_AB[a][b], a in A, b in B
-          const int pl = 3 * (2 * (a >> 3) + (b >> 3)), e = (a & 7) * 8 + (b & 7);
-          v = make_double2(S.red[0][pl][e], S.red[0][pl + 1][e] - S.red[0][pl + 2][e]);
-          if (hp) v.y = -v.y;                                           // lower block = conjugate transpose
-        }
-      } else if (!within) {
-        v = (hp == 0 || blkB >= 0) ? __ldcg((hp ? wdB : wdA) + (p & 15) * 16 + (q & 15)) : make_double2(0.0, 0.0);
-      }
-      S.W[p * W32 + q] = v;
-      S.Q[p * W32 + q] = make_double2(p == q ? 1.0 : 0.0, 0.0);
-    }
-  }
-  __syncthreads();
-  if (within) {   // the first step of a tournament recomputes the two travelling Gram blocks from the columns
-    gram16_diag(S, G, ldg, M, S.cols, 0, tid);
-    if (blkB >= 0) gram16_diag(S, G, ldg, M, S.cols + 16, 16, tid);
-  }
-  // convergence test over the pairs this task is responsible for
-  {
-    int need = 0;
-    for (int i = tid; i < 1024; i += JT16) {
-      const int p = i >> 5, q = i & 31;
-      if (p < q && (within || (p < 16 && q >= 16))) {
-        const double a = S.W[p * W32 + p].x, b = S.W[q * W32 + q].x;
-        const double2 g = S.W[p * W32 + q];
-        if (a > dead_abs && b > dead_abs && (g.x * g.x + g.y * g.y) > tol2 * a * b) need = 1;
-      }
-    }
-    if (need) S.need = 1;
-  }
-  __syncthreads();
-  if (timing) { tC = clock64(); atomicAdd(&g_phase_cycles[0], (unsigned long long)(tC - tA)); atomicAdd(&g_phase_cycles[5], 1ull); }
-  const unsigned long long gram_flops = (unsigned long long)((M + 3) >> 2) * (within ? 18432ull : 8192ull);
-  if (!S.need) {
-    if (tid < 32 && S.cols[tid] >= 0) P.cn2[S.cols[tid]] = S.W[tid * W32 + tid].x;
-    if (!within && tid == 0) {
-      const int va = blkA < blkB ? verA : verB, vb = blkA < blkB ? verB : verA;
-      *recp = make_int2(va + 1, vb + 1);
-    }
-    if (within) {
-      for (int i = tid; i < 512; i += JT16) {
-        const int bb = i >> 8, r = (i >> 4) & 15, c = i & 15;
-        if (bb == 0 || blkB >= 0) P.wd[(size_t)(bb ? blkB : blkA) * 256 + r * 16 + c] = S.W[(16 * bb + r) * W32 + 16 * bb + c];
-      }
-    }
-    if (tid == 0) atomicAdd(&g_dmma_flops, gram_flops);
-    return;
-  }
-  if (tid == 0) { dirty[mat] = 1; atomicAdd(&g_dmma_flops, gram_flops + (unsigned long long)((M + 7) >> 3) * 65536ull); }
-
-  // ------------------------------------------------------------------ phase B: 16 (31) rounds of 16 disjoint rotations
-  {
-    const int nrounds = within ? 31 : 16;
-    for (int r = 0; r < nrounds; ++r) {
-      int rot = 0;
-      if (tid < 16) {
-        int p, q;
-        jacobi_pair32(r, tid, p, q);
-        const double a = S.W[p * W32 + p].x, b = S.W[q * W32 + q].x;
-        const double2 g = S.W[p * W32 + q];
-        const double g2 = g.x * g.x + g.y * g.y;
-        double c = 1.0;
-        double2 sg = make_double2(0.0, 0.0);
-        if (a > dead_abs && b > dead_abs && g2 > tol2 * a * b) {
-          rot = 1;
-          const double d = b - a;
-          const double rh = rsqrt(d * d + 4.0 * g2);
-          const double x = 0.5 * (1.0 + fabs(d) * rh);
-          const double rx = rsqrt(x);
-          c = x * rx;
-          sg = rmul(d >= 0.0 ? rh * rx : -(rh * rx), g);
-        }
-        S.rc[tid] = c; S.rs[tid] = sg; S.rp[tid] = p; S.rq[tid] = q;
-      }
-      if (!__syncthreads_or(rot)) continue;
-      // W <- J^H W J: 16 x 16 pair blocks
-#pragma unroll
-      for (int k = 0; k < 256 / JT16; ++k) {
-        const int blk = tid + JT16 * k;
-        const int ia = blk >> 4, ib = blk & 15;
-        const int pa = S.rp[ia], qa = S.rq[ia], pb = S.rp[ib], qb = S.rq[ib];
-        const double ca = S.rc[ia], cb = S.rc[ib];
-        const double2 sa = S.rs[ia], sb = S.rs[ib];
-        const double2 w00 = S.W[pa * W32 + pb], w01 = S.W[pa * W32 + qb], w10 = S.W[qa * W32 + pb], w11 = S.W[qa * W32 + qb];
-        const double2 t00 = csub(rmul(ca, w00), cmul(sa, w10));
-        const double2 t01 = csub(rmul(ca, w01), cmul(sa, w11));
-        const double2 t10 = cadd(cmulc(sa, w00), rmul(ca, w10));
-        const double2 t11 = cadd(cmulc(sa, w01), rmul(ca, w11));
-        S.W[pa * W32 + pb] = csub(rmul(cb, t00), cmulc(sb, t01));
-        S.W[pa * W32 + qb] = cadd(cmul(sb, t00), rmul(cb, t01));
-        S.W[qa * W32 + pb] = csub(rmul(cb, t10), cmulc(sb, t11));
-        S.W[qa * W32 + qb] = cadd(cmul(sb, t10), rmul(cb, t11));
-      }
-      // Q <- Q J: 32 rows x 16 pairs
-#pragma unroll
-      for (int k = 0; k < 512 / JT16; ++k) {
-        const int it = tid + JT16 * k;
-        const int row = it >> 4, ia = it & 15;
-        const int pa = S.rp[ia], qa = S.rq[ia];
-        const double ca = S.rc[ia];
-        const double2 sa = S.rs[ia];
-        const double2 x = S.Q[row * W32 + pa], y = S.Q[row * W32 + qa];
-        S.Q[row * W32 + pa] = csub(rmul(ca, x), cmulc(sa, y));
-        S.Q[row * W32 + qa] = cadd(cmul(sa, x), rmul(ca, y));
-      }
-      __syncthreads();
-    }
-  }
-  if (timing) { tD = clock64(); atomicAdd(&g_phase_cycles[2], (unsigned long long)(tD - tC)); }
-  if (tid < 32 && S.cols[tid] >= 0) P.cn2[S.cols[tid]] = S.W[tid * W32 + tid].x;
-  if (tid == 0) {
-    if (within) { verA = __ldcg(P.ver + blkA); if (blkB >= 0) verB = __ldcg(P.ver + blkB); }
-    P.ver[blkA] = verA + 1;
-    if (blkB >= 0) P.ver[blkB] = verB + 1;
-  }
-  for (int i = tid; i < 512; i += JT16) {
-    const int bb = i >> 8, r = (i >> 4) & 15, c = i & 15;
-    if (bb == 0 || blkB >= 0) P.wd[(size_t)(bb ? blkB : blkA) * 256 + r * 16 + c] = S.W[(16 * bb + r) * W32 + 16 * bb + c];
-  }
-
-  // ------------------------------------------------------------------ phase C: X <- X Q (32 columns) on DMMA, in place
-  {
-    const double2* qbase = S.Q + (lane & 3) * W32 + (lane >> 2);   // B fragment (k4, jn) = qbase[4 k4 W32 + 8 jn]
-    const double2* src[8];
-#pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4) {
-      const int c = S.cols[4 * k4 + (lane & 3)];
-      src[k4] = (c >= 0) ? G + (size_t)ldg * c : nullptr;
-    }
-    const int nch = (M + 7) >> 3;
-    for (int ch = warp; ch < nch; ch += NW16) {
-      const int row = 8 * ch + (lane >> 2);
-      double2 xa[8];
-#pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) xa[k4] = (row < M && src[k4]) ? __ldcg(src[k4] + row) : make_double2(0.0, 0.0);
-      double re[4][2], im[4][2];
-#pragma unroll
-      for (int jn = 0; jn < 4; ++jn) { re[jn][0] = re[jn][1] = im[jn][0] = im[jn][1] = 0.0; }
-#pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-        const double ar = xa[k4].x, ai = xa[k4].y, nai = -ai;
-#pragma unroll
-        for (int jn = 0; jn < 4; ++jn) {
-          const double2 qv = qbase[4 * k4 * W32 + 8 * jn];
-          dmma884(re[jn][0], re[jn][1], ar, qv.x);
-          dmma884(im[jn][0], im[jn][1], ar, qv.y);
-          dmma884(re[jn][0], re[jn][1], nai, qv.y);
-          dmma884(im[jn][0], im[jn][1], ai, qv.x);
-        }
-      }
-      if (row < M) {
-#pragma unroll
-        for (int jn = 0; jn < 4; ++jn)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = S.cols[8 * jn + 2 * (lane & 3) + e];
-            if (c >= 0) G[(size_t)ldg * c + row] = make_double2(re[jn][e], im[jn][e]);
-          }
-      }
-    }
-  }
-  if (timing) { atomicAdd(&g_phase_cycles[3], (unsigned long long)(clock64() - tD)); atomicAdd(&g_phase_cycles[6], 1ull); }
-}
-
-// persistent dataflow sweep over 16-column blocks (see jacobi_sweep_kernel for the scheme)
-__global__ void __launch_bounds__(JT16, 2) jacobi_sweep16_kernel(const JacobiProblem* __restrict__ probs, int batch, int max_pairs, int nsteps,
-                                                               int base, double tol2, double dead2, const double* __restrict__ fro2,
-                                                               int* __restrict__ dirty, const int* __restrict__ done,
-                                                               int* __restrict__ progress, int progress_stride, int* __restrict__ counter,
-                                                               int* __restrict__ fault) {
-  extern __shared__ __align__(16) unsigned char dyn_smem16[];
-  Smem16& S = *reinterpret_cast<Smem16*>(dyn_smem16);
-  __shared__ int s_task;
-  const int per_step = batch * max_pairs;
-  const int total = nsteps * per_step;
-  for (;;) {
-    if (threadIdx.x == 0) s_task = atomicAdd(counter, 1);
-    __syncthreads();
-    const int t = s_task;
-    __syncthreads();
-    if (t >= total) return;
-    const int step = t / per_step, r = t - step * per_step;
-    const int mat = r / max_pairs, pi = r - mat * max_pairs;
-    if (done[mat]) continue;
-    const JacobiProblem P = probs[mat];
-    const int npairs = (P.nb == 1) ? 1 : P.nbe / 2;
-    if (pi >= npairs) continue;
-    int blkA, blkB;
-    bool within;
-    if (!pair_blocks(P, step, pi, blkA, blkB, within)) continue;
-    int* prog = progress + (size_t)mat * progress_stride;
-    if (threadIdx.x == 0) {
-      const long long tw = (g_dbg_mode == 10) ? clock64() : 0;
-      const int need = base + step;
-      unsigned spins = 0;
-      while (ld_acquire(prog + blkA) < need && ++spins < (1u << 23)) __nanosleep(64);
-      if (blkB >= 0)
-        while (ld_acquire(prog + blkB) < need && ++spins < (1u << 23)) __nanosleep(64);
-      if (spins >= (1u << 23)) atomicAdd(fault, 1);
-      if (g_dbg_mode == 10) atomicAdd(&g_phase_cycles[4], (unsigned long long)(clock64() - tw));
-    }
-    __syncthreads();
-    pair_task16(S, P, mat, blkA, blkB, within, tol2, dead2, fro2, dirty);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      st_release(prog + blkA, base + step + 1);
-      if (blkB >= 0) st_release(prog + blkB, base + step + 1);
-    }
-  }
-}
-
-// fro2[m] += ||G_m||_F^2 (slice blockIdx.x of 16); fro2 must be zeroed before the launch
 __global__ void __launch_bounds__(256) fro2_kernel(const JacobiProblem* __restrict__ probs, double* __restrict__ fro2) {
   const JacobiProblem P = probs[blockIdx.y];
   const size_t total = (size_t)P.M * P.N;   // ldg == M
@@ -910,26 +451,6 @@ __global__ void __launch_bounds__(256) fro2_kernel(const JacobiProblem* __restri
     __syncthreads();
   }
   if (threadIdx.x == 0 && sh[0] != 0.0) atomicAdd(fro2 + blockIdx.y, sh[0]);
-}
-
-__global__ void __launch_bounds__(256) jacobi_thr_kernel(const JacobiProblem* __restrict__ probs, int keep, double margin,
-                                                         const int* __restrict__ done) {
-  const int mat = blockIdx.x;
-  if (done[mat]) return;
-  const JacobiProblem P = probs[mat];
-  if (P.N <= keep) return;   // nothing will be truncated by max-bond-dim: rule stays off
-  extern __shared__ double s_cn[];
-  for (int i = threadIdx.x; i < P.N; i += 256) s_cn[i] = P.cn2[i];
-  __syncthreads();
-  for (int k = threadIdx.x; k < P.N; k += 256) {
-    const double v = s_cn[k];
-    int rank = 0;
-    for (int j = 0; j < P.N; ++j) {
-      const double w = s_cn[j];
-      rank += (w > v || (w == v && j < k)) ? 1 : 0;
-    }
-    if (rank == keep - 1) *P.thr = margin * v;
-  }
 }
 
 // After a sweep: a matrix that went through it without a rotation is done.  Also compacts the matrices still rotating into
@@ -1050,48 +571,18 @@ __global__ void gather_kernel(const GatherProblem* __restrict__ probs) {
 
 }  // namespace
 
-static bool g_use_3m = false;   // measured on B200: the column update is L2-bandwidth-bound, 3M does not pay (profiles/)
-void jacobi_set_3m(int on) { g_use_3m = on != 0; }
-void launch_jacobi_step(const JacobiProblem* d_probs, int batch, int max_pairs, int step, double tol2, double dead2,
-                        const double* d_fro2, int* d_dirty, const int* d_done, cudaStream_t s) {
-  if (batch <= 0) return;
-  dim3 grid(max_pairs, batch);
-  if (g_use_3m) jacobi_step_kernel<true><<<grid, JT, 0, s>>>(d_probs, step, tol2, dead2, d_fro2, d_dirty, d_done);
-  else jacobi_step_kernel<false><<<grid, JT, 0, s>>>(d_probs, step, tol2, dead2, d_fro2, d_dirty, d_done);
-}
 void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
                          const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
-                         int* d_fault, int grid_ctas, int warps_per_task, int stagger_ns, const int* d_active, cudaStream_t s) {
+                         int* d_fault, int grid_ctas, int warps_per_task, const int* d_active, cudaStream_t s) {
   if (batch <= 0) return;
-  const long total = (long)nsteps * batch * max_pairs;   // batch = matrices still rotating when d_active is given
+  const long total = (long)nsteps * batch * max_pairs;   // batch = upper bound of the matrices still rotating (d_active[0] on the device)
   const int grid = (int)std::min<long>(total, grid_ctas);
   if (warps_per_task == 8)
-    jacobi_sweep_kernel<false, 8><<<grid, 256, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
-                                                      d_progress, progress_stride, d_counter, d_fault, stagger_ns, d_active);
-  else if (g_use_3m)
-    jacobi_sweep_kernel<true, 4><<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
-                                                     d_progress, progress_stride, d_counter, d_fault, stagger_ns, d_active);
+    jacobi_sweep_kernel<8><<<grid, 256, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
+                                               d_progress, progress_stride, d_counter, d_fault, d_active);
   else
-    jacobi_sweep_kernel<false, 4><<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
-                                                      d_progress, progress_stride, d_counter, d_fault, stagger_ns, d_active);
-}
-void launch_jacobi_sweep16(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
-                           const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
-                           int* d_fault, int n_sm, cudaStream_t s) {
-  if (batch <= 0) return;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(jacobi_sweep16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem16));
-    attr = true;
-  }
-  const long total = (long)nsteps * batch * max_pairs;
-  const int grid = (int)std::min<long>(total, (long)n_sm * 2);
-  jacobi_sweep16_kernel<<<grid, JT16, sizeof(Smem16), s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
-                                                         d_progress, progress_stride, d_counter, d_fault);
-}
-void launch_jacobi_thr(const JacobiProblem* d_probs, int batch, int keep, double margin, const int* d_done, cudaStream_t s) {
-  if (batch <= 0 || keep <= 0 || margin <= 0.0) return;
-  jacobi_thr_kernel<<<batch, 256, 48 * 1024, s>>>(d_probs, keep, margin, d_done);
+    jacobi_sweep_kernel<4><<<grid, JT, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
+                                              d_progress, progress_stride, d_counter, d_fault, d_active);
 }
 double jacobi_dmma_flops() {
   unsigned long long v = 0;

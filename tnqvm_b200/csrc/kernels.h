@@ -47,8 +47,7 @@ struct QrProblem {
   double2* G;
   int M, N, ldy;
 };
-// side/ev (4 timing-disabled events) enable the two-stream look-ahead schedule; pass nullptr for a single stream
-void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaStream_t s, cudaStream_t side, cudaEvent_t* ev);
+void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaStream_t s);
 int qr_launch_count(int max_n);
 
 // ---------------------------------------------------------------------------------------------
@@ -58,33 +57,20 @@ struct JacobiProblem {
   int M, N, ldg;
   int nb;    // column blocks of 8 (ceil(N/8))
   int nbe;   // nb rounded up to even (>= 2) ; 1 when nb == 1
-  // discard-aware rotation rule: cn2[N] = current squared column norms (written by the pair tasks); *thr = a fraction of
-  // the keep-th largest of them (jacobi_thr_kernel, once per sweep; 0 = rule off).  Two columns that are both below
-  // *thr are both certain to be truncated and need not be orthogonalised against each other.
-  double* cn2;
-  double* thr;
   double2* wd;   // nb travelling 8x8 Gram blocks (row-major, 64 complex each): W_BB of every column block
   int* ver;      // nb block versions (rotations seen), zeroed per SVD
   int2* rec;     // nbe x nbe clean-pair memo: versions (+1) of (A < B) at which their cross pairs were last found clean; zeroed per SVD
 };
-// per sweep: *thr = margin * (keep-th largest cn2) for every matrix with N > keep that is still rotating
-void launch_jacobi_thr(const JacobiProblem* d_probs, int batch, int keep, double margin, const int* d_done, cudaStream_t s);
-void launch_jacobi_step(const JacobiProblem* d_probs, int batch, int max_pairs, int step, double tol2, double dead2,
-                        const double* d_fro2, int* d_dirty, const int* d_done, cudaStream_t s);
-// one whole sweep (nsteps steps) in one persistent launch; d_progress: per matrix `progress_stride` ints (>= nbe), zeroed once
-// per SVD; base = steps completed by the previous sweeps; *d_counter zeroed (one counter per launch)
+// one whole sweep (nsteps tournament steps) in one persistent launch; d_progress: per matrix `progress_stride` ints (>= nbe), zeroed once
+// per SVD; base = steps completed by the previous sweeps; *d_counter zeroed (one counter per launch).  d_active: [0] = matrices
+// still rotating (read on the device: the host's `batch` is only an upper bound used to size the grid), [1..] their indices.
 void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
                          const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
-                         int* d_fault, int grid_ctas, int warps_per_task /* 4 or 8 */, int stagger_ns,
-                         const int* d_active /* optional: [0] = matrices still rotating (= batch), [1..] their indices */, cudaStream_t s);   // *d_fault += 1 if a dependency wait timed out
-// the same sweep over 16-column blocks (JacobiProblem.nb / nbe count 16-column blocks, wd holds 256 complex per block)
-void launch_jacobi_sweep16(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
-                           const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
-                           int* d_fault, int n_sm, cudaStream_t s);
+                         int* d_fault /* += 1 if a dependency wait timed out */, int grid_ctas, int warps_per_task /* 4 or 8 */,
+                         const int* d_active, cudaStream_t s);
 void jacobi_set_debug_mode(int mode);   // timing experiments only
 void jacobi_print_phase_timing();
-void jacobi_set_3m(int on);   // 3M complex product in the column update (default off); process-wide
-double jacobi_dmma_flops();   // process-wide count of real flops the Jacobi pair tasks issued on the DMMA pipe
+double jacobi_dmma_flops();   // process-wide count of the FP64 flops the Jacobi pair tasks executed (Gram on DMMA + scaled rotations)
 void launch_fro2(const JacobiProblem* d_probs, int batch, double* d_fro2, cudaStream_t s);   // d_fro2 pre-zeroed
 // after a sweep: done[m] |= !dirty[m]; dirty[m] = 0; *remaining = #not done
 void launch_jacobi_check(int batch, int* d_dirty, int* d_done, int* d_remaining, int* d_active /* may be null */, cudaStream_t s);

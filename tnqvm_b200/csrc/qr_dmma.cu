@@ -368,12 +368,7 @@ __global__ void __launch_bounds__(256) qr_rh_kernel(const QrProblem* __restrict_
 
 }  // namespace
 
-// Look-ahead schedule on two streams: the main stream factors panel k+1 as soon as its 16 columns have seen update k, while
-// the side stream applies update k to the rest of the trailing matrix:
-//   main: panel(k) -> [wait rest(k-1)] -> update(k, next panel's columns) -> panel(k+1) ...
-//   side: [wait panel(k)] -> update(k, the rest)
-// `ev` must hold 4 events (timing disabled).
-void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaStream_t s, cudaStream_t side, cudaEvent_t* ev) {
+void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaStream_t s) {
   if (batch <= 0 || max_n <= 0) return;
   // the panel is staged in shared memory whenever it fits (the kernel applies the same test per matrix)
   const size_t want = (size_t)max_m * PB * sizeof(double2);
@@ -384,40 +379,19 @@ void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaSt
     attr_set = true;
   }
   const int npanels = (max_n + PB - 1) / PB;
-  const bool two = side != nullptr && ev != nullptr && npanels > 2;
-  if (two) {   // the side stream starts behind everything already queued on the main stream
-    cudaEventRecord(ev[2], s);
-    cudaStreamWaitEvent(side, ev[2], 0);
-  }
   for (int k = 0; k < npanels; ++k) {
     qr_panel_kernel<<<batch, PT, smem, s>>>(d_probs, k);
     const int ntr = max_n - (k + 1) * PB;
     if (ntr <= 0) break;
-    if (!two) {
-      dim3 grid((ntr + SLAB - 1) / SLAB, batch);
-      qr_update_kernel<<<grid, UT, 0, s>>>(d_probs, k, 0, 1 << 30);
-      continue;
-    }
-    cudaEventRecord(ev[0], s);                       // panel k done
-    if (ntr > PB) {
-      cudaStreamWaitEvent(side, ev[0], 0);
-      dim3 grid((ntr - PB + SLAB - 1) / SLAB, batch);
-      qr_update_kernel<<<grid, UT, 0, side>>>(d_probs, k, PB, 1 << 30);
-    }
-    if (k > 0) cudaStreamWaitEvent(s, ev[1], 0);     // rest(k-1) done: the next panel's columns are current up to step k-1
-    if (ntr > PB) cudaEventRecord(ev[1], side);      // rest(k) done
-    qr_update_kernel<<<dim3(1, batch), UT, 0, s>>>(d_probs, k, 0, PB);
-  }
-  if (two) {
-    cudaEventRecord(ev[3], side);
-    cudaStreamWaitEvent(s, ev[3], 0);
+    dim3 grid((ntr + SLAB - 1) / SLAB, batch);
+    qr_update_kernel<<<grid, UT, 0, s>>>(d_probs, k, 0, 1 << 30);
   }
   dim3 g2((max_n + 31) / 32, (max_n + 31) / 32, batch);
   qr_rh_kernel<<<g2, 256, 0, s>>>(d_probs);
 }
 int qr_launch_count(int max_n) {
   const int npanels = (max_n + PB - 1) / PB;
-  return 3 * npanels - 2;   // panels + look-ahead and trailing updates (the last panel has none) + the R^H transpose
+  return 2 * npanels;   // panels + trailing updates (the last panel has none) + the R^H transpose
 }
 
 }  // namespace mpsb200

@@ -13,6 +13,8 @@ def gate_matrix(name, params=()):
     p = list(params) + [0.0, 0.0, 0.0]
     if name == "CX":
         name = "CNOT"
+    if name == "U3":
+        name = "U"
     one = {
         "I": lambda: [[1, 0], [0, 1]],
         "H": lambda: [[_S2, _S2], [_S2, -_S2]],
@@ -22,6 +24,8 @@ def gate_matrix(name, params=()):
         "Rx": lambda: [[math.cos(0.5 * p[0]), -1j * math.sin(0.5 * p[0])], [-1j * math.sin(0.5 * p[0]), math.cos(0.5 * p[0])]],
         "Ry": lambda: [[math.cos(0.5 * p[0]), -math.sin(0.5 * p[0])], [math.sin(0.5 * p[0]), math.cos(0.5 * p[0])]],
         "Rz": lambda: [[cmath.exp(-0.5j * p[0]), 0], [0, cmath.exp(0.5j * p[0])]],
+        "S": lambda: [[1, 0], [0, 1j]],
+        "Sdg": lambda: [[1, 0], [0, -1j]],
         "T": lambda: [[1, 0], [0, cmath.exp(0.25j * math.pi)]],
         "Tdg": lambda: [[1, 0], [0, cmath.exp(-0.25j * math.pi)]],
         "U": lambda: [[math.cos(p[0] / 2), -cmath.exp(1j * p[2]) * math.sin(p[0] / 2)],

@@ -243,8 +243,8 @@ class B200MPS:
         return p.value or 0
 
     def stats(self):
-        out = np.zeros(11, dtype=np.float64)
-        self._ck(self.L.mps_stats(self.h, out.ctypes.data, 11))
+        out = np.zeros(13, dtype=np.float64)
+        self._ck(self.L.mps_stats(self.h, out.ctypes.data, 13))
         keys = ["gates_2q", "gates_1q_kernel", "layers", "jacobi_sweeps", "launches", "ms_theta", "ms_svd", "ms_writeback", "ms_qr",
-                "jacobi_dmma_flops", "gates_2q_fused"]
+                "jacobi_dmma_flops", "gates_2q_fused", "svd_nonconverged", "norm_guard_violations"]
         return dict(zip(keys, out.tolist()))
