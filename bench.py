@@ -47,9 +47,9 @@ def parse_args():
     ap.add_argument("--chi", type=int, default=256)
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--gauge", type=int, default=0)
-    ap.add_argument("--cpu-sample-gates", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the chi=512 theta line, the visitor-path run and the sharded circuit")
     ap.add_argument("--no-peak", action="store_true", help="skip the live cuBLAS DGEMM peak measurement (profiling runs)")
     ap.add_argument("--no-qr", action="store_true", help="A/B: disable the QR pre-reduction of the SVD")
     ap.add_argument("--jacobi-tol", type=float, default=0.0, help="A/B: override the Jacobi convergence tolerance")
@@ -184,23 +184,12 @@ def run_reference(args):
     o = O.OracleMPS(n, max_bond=chi, gesdd=True, gauge=args.gauge)
     for k, t in enumerate(random_mps_sites(n, chi, args.seed)):
         o.set_site(k, t)
-    G = args.cpu_sample_gates
-    mid = n // 2
-
     def one_step(i):
-        circ = step_circuit(n, i, args.seed)
-        # bounded sample: the G saturated-bond CNOTs nearest the middle of the chain (alternating layer parity)
-        # together with the 1q gates on their qubits
-        lo0 = (mid - G) // 2 * 2 + (i & 1)
-        pairs = [(lo0 + 2 * j, lo0 + 2 * j + 1) for j in range(G)]
-        qs = {q for p in pairs for q in p}
+        # the SAME step the B200 arm times: two brickwork layers, all 2n 1q gates and all n-1 CNOTs
         n2 = 0
-        for g in circ[:n]:
-            if g[1][0] in qs:
-                o.apply(g[0], g[1], g[2])
-        for p in pairs:
-            o.apply("CNOT", p, ())
-            n2 += 1
+        for g in step_circuit(n, i, args.seed):
+            o.apply(g[0], g[1], g[2])
+            n2 += len(g[1]) == 2
         return n2
 
     for i in range(args.warmup):
@@ -211,11 +200,13 @@ def run_reference(args):
         n2 += one_step(args.warmup + i)
     dt = time.perf_counter() - t0
     val = n2 / dt
-    sample = "%d saturated-bond CNOTs (+ their 1q gates) per step near the chain centre of a random chi=%d %d-qubit MPS; zgemm+zgesdd (scipy OpenBLAS)" % (G, chi, n)
+    sample = ("the full step of the B200 arm (2 brickwork layers: %d 1q + %d 2q gates, chain ends included) on a random chi=%d-saturated "
+              "%d-qubit MPS; zgemm+zgesdd (scipy OpenBLAS)" % (2 * n, n - 1, chi, n))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "c128", "data": "synthetic",
             "config": {"workload": "c2_brickwork_n%d_chi%d" % (n, chi), "qubits": n, "max_bond_dim": chi, "gauge": "reference" if args.gauge == 0 else "canonical",
+                       "step": "2 brickwork layers = %d 1q + %d 2q gates on the saturated state" % (2 * n, n - 1), "same_step_as_b200_arm": True,
                        "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -368,6 +359,50 @@ def run_b200(args):
         e2e = {"value": world * args.steps * n2_step / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes + 8 * (n + 1), "ms_per_step": dt / args.steps * 1e3}
 
+    # ---- north_star target line: theta contraction at chi >= 512 against the FP64 peak (24-qubit chain, random saturated sites)
+    theta512 = None
+    if rank == 0 and not args.no_extras and chi < 512:
+        n5, chi5 = 24, 512
+        e5 = tnqvm_b200.B200MPS(n5, max_bond=chi5, device=local)
+        for k, t in enumerate(random_mps_sites(n5, chi5, seed)):
+            e5.set_site(k, t)
+        st5 = [tnqvm_b200.CompiledCircuit(step_circuit(n5, i, seed)) for i in range(4)]
+        for i in range(2):
+            e5.run(st5[i]); e5.flush()
+        e5.sync()
+        b5 = list(e5.bond_dims())
+        e5.set_option("profile", 1)
+        q0 = e5.stats()
+        fl5 = 0.0
+        for i in range(2, 4):
+            fl5 += gate_flops(b5, n5, step_circuit(n5, i, seed))[0]
+            e5.run(st5[i]); e5.flush()
+        e5.sync()
+        q1 = e5.stats()
+        e5.close()
+        ms5 = q1["ms_theta"] - q0["ms_theta"]
+        tf5 = fl5 / (ms5 * 1e-3) / 1e12 if ms5 > 0 else None
+        theta512 = {"bound": "tensor", "kernel": "zgemm_dmma_kernel<theta>", "workload": "24-qubit chain, chi=512, 2 steps", "achieved": tf5, "peak": fp64_peak,
+                    "unit": "TFLOP/s", "frac": (tf5 / fp64_peak) if (tf5 and fp64_peak) else None,
+                    "ms_per_step": {"theta": ms5 / 2, "svd": (q1["ms_svd"] - q0["ms_svd"]) / 2, "writeback": (q1["ms_writeback"] - q0["ms_writeback"]) / 2}}
+
+    # ---- the same depth-D circuit through the reference-facing C++ surface: XASM text -> TNQVM::execute restated
+    # (b200_tnqvm_run: setOptions, initialize, nearest-neighbour pass, visit() per instruction, finalize with the norm)
+    e2e_visitor = None
+    drv = os.path.join(ROOT, "tnqvm_b200", "lib", "b200_tnqvm_run")
+    if rank == 0 and not args.no_extras and os.path.exists(drv):
+        xasm = Cc.to_xasm(circ0)
+        try:
+            r = subprocess.run([drv, "--xasm", "-", "--qubits", str(n), "--max-bond-dim", str(chi), "--device", str(local), "--repeat", "3"],
+                               input=xasm, capture_output=True, text=True, timeout=300)
+            doc = json.loads(r.stdout.strip().splitlines()[-1])
+            wall = min(doc["execute_ms"][1:])
+            e2e_visitor = {"circuit_wall_ms": wall, "gates_2q_per_s": n2_0 / (wall * 1e-3), "norm": doc.get("norm"),
+                           "path": "XASM -> B200MpsVisitor::initialize/visit()/finalize via b200_tnqvm_run (host wall clock, second and third execute() on one visitor instance)",
+                           "device_timed_same_circuit_ms": circuit_ms}
+        except Exception as ex:   # reported, never silently dropped
+            e2e_visitor = {"error": repr(ex)[:300]}
+
     # ---- CPU baseline beside it (rank 0, N = 1): the oracle on a bounded sample of the same step, same state
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -377,21 +412,14 @@ def run_b200(args):
         o = O.OracleMPS(n, max_bond=chi, gesdd=True, gauge=args.gauge)
         for k in range(n):
             o.set_site(k, eng.get_site(k))
-        G = args.cpu_sample_gates
-        lo0 = (n // 2 - G) // 2 * 2
-        pairs = [(lo0 + 2 * j, lo0 + 2 * j + 1) for j in range(G)]
-        qs = {q for p in pairs for q in p}
         circ = steps[-1]
-        o.apply("CNOT", pairs[0], ())   # warm the BLAS threads
+        o.apply("CNOT", (n // 2, n // 2 + 1), ())   # warm the BLAS threads
         t0 = time.perf_counter()
-        for g in circ[:n]:
-            if g[1][0] in qs:
-                o.apply(g[0], g[1], g[2])
-        for p in pairs:
-            o.apply("CNOT", p, ())
+        for g in circ:
+            o.apply(g[0], g[1], g[2])
         dt = time.perf_counter() - t0
-        cpu = {"value": G / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d saturated-bond (chi=%d) CNOTs + their 1q gates of one step on the GPU run's own state; oracle zgemm+zgesdd, scipy OpenBLAS" % (G, chi)}
+        cpu = {"value": n2_step / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "one full step (%d 1q + %d 2q gates, the step the GPU arm times) on the GPU run's own chi=%d state; oracle zgemm+zgesdd, scipy OpenBLAS" % (2 * n, n2_step, chi)}
 
     if rank == 0:
         traffic = None
@@ -426,6 +454,8 @@ def run_b200(args):
                                    "jacobi_sweeps_per_layer": sweeps_per_layer},
             "circuit": {"name": "brickwork n=%d depth=%d chi<=%d from |0>" % (n, args.depth, chi), "wall_ms": circuit_ms, "gates_1q": n1_0, "gates_2q": n2_0,
                         "gates_2q_per_s": n2_0 / (circuit_ms * 1e-3), "launches": int(st1["launches"] - st0["launches"])},
+            "roofline_theta_chi512": theta512,
+            "e2e_visitor": e2e_visitor,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

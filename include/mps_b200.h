@@ -40,6 +40,19 @@ typedef struct mps_b200_handle* mps_handle_t;
  * = register*n_qubits + q); independent circuits then share batched kernel launches (config 4). */
 int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, int gauge, int device,
                uint64_t seed, mps_handle_t* out);
+/* The MPI site-block scheme of the reference (process groups and block ownership ExaTnMpsVisitor.cpp:347-531, boundary 2q-gate
+ * dispatch :2059-2170, finalize gather :685-696) as ONE process driving several GPUs of a box: the sites are split into
+ * contiguous blocks, one per device (partition_by_cost != 0: blocks of equal estimated SVD cost on the saturated bond profile
+ * of max_bond; otherwise equal counts -- one formula, the reference's two disagree when n % P != 0).  Each device runs its own
+ * engine on its own stream and host thread; the gates of a dependency layer execute concurrently on all devices.  A gate on a
+ * block boundary is executed by the owner of its LEFT site: the right owner's boundary tensor travels there and back as one
+ * peer copy over NVLink each way (32 chi^2 bytes, ordered by CUDA events; no host staging, no collective).  Every other entry
+ * point of this header works on such a handle unchanged (qubit indices are global).  n_devices == 1 is mps_create.  A device
+ * may be listed more than once (its blocks then share that GPU: how the single-GPU tests exercise the exchange logic). */
+int mps_create_sharded(int n_qubits, int max_bond, double svd_cutoff, int gauge, int n_devices, const int* devices,
+                       int partition_by_cost, uint64_t seed, mps_handle_t* out);
+/* device blocks of a handle: *n_devices, and first_site[d] for d = 0..n_devices (first_site[n_devices] = n_qubits; may be NULL) */
+int mps_shard_layout(mps_handle_t h, int* n_devices, int* first_site);
 int mps_destroy(mps_handle_t h);
 const char* mps_last_error(mps_handle_t h); /* h may be NULL: last mps_create error */
 int mps_reset(mps_handle_t h);              /* back to |0...0>, ExaTnMpsVisitor.cpp:273-326 */
@@ -51,13 +64,15 @@ int mps_restore(mps_handle_t h);
 
 /* keys: "max_bond", "svd_cutoff", "gauge" (as in mps_create), "cutoff_on_sqrt" (computePartialNormsSync ambiguity,
  * SURVEY 8c), "fuse_1q", "fuse_2q" (default 0: merge consecutive 2q gates on one site pair into one 4x4 -- fewer SVDs, but with
- * truncation active no longer truncation-for-truncation identical to the reference), "renormalize", "jacobi_tol", "null_tol", "jacobi_max_sweeps", "profile", "layer_batch" (0 = execute
- * gate by gate).  Engine variants kept for A/B measurements, all parity-tested (tests/test_gpu_parity.py): "qr_prereduce"
- * (default 1), "jacobi_persistent" (1: one dataflow launch per sweep; 0: one launch per tournament step), "jacobi_groups"
- * (stream groups of the per-step path), "jacobi_block16" (0: 8-column blocks; 1: 16-column blocks), "jacobi_3m" (0; process
- * wide), "discard_margin" (0 = off), "qr_lookahead" (0), "jacobi_ctas_per_sm" (0 = by load: as many resident CTAs of the
- * persistent sweep kernel as a tournament step has pair tasks, 1..4 per SM), "jacobi_wide_tasks" (1: eight warps per pair task
- * when at most two tasks per SM are resident, the few-gates-per-layer regime of routed circuits; 0: always four). */
+ * truncation active no longer truncation-for-truncation identical to the reference), "renormalize", "jacobi_tol", "null_tol", "jacobi_max_sweeps" (1..1000; matrices still rotating after that many sweeps are counted in mps_stats[11]), "profile",
+ * "layer_batch" (0 = execute gate by gate), "norm_guard" (post-SVD check of ExaTnMpsVisitor.cpp:1632-1661: 2 = the reference's
+ * Release-build behaviour (default): report once on stderr, count in mps_stats[12]; 1 = its Debug-build behaviour: the call fails;
+ * 0 = off), "null_tol" (components with sigma <= null_tol * sigma_max are treated as the exact zeros they
+ * stand for and dropped; <= 0 (default): 10 x the Jacobi tolerance.  A documented deviation: LAPACK inside ExaTN keeps them as noise).  Options that change how queued gates execute flush the queue first.
+ * Engine variants kept for A/B measurements, all parity-tested (tests/test_gpu_parity.py): "qr_prereduce" (default 1),
+ * "jacobi_ctas_per_sm" (0 = by load, 1..4), "jacobi_wide_tasks" (1: eight warps per pair task when at most two tasks per SM
+ * are resident), "jacobi_chunk_mb" (Jacobi work matrices of a layer run in chunks of at most this many MiB so that a chunk
+ * stays L2-resident over its sweeps), "l2_persist" (persisting-L2 access window over the running chunk). */
 int mps_set_option(mps_handle_t h, const char* key, double value);
 
 /* applyGate 1q branch, ExaTnMpsVisitor.cpp:1185-1292.  m = row-major 2x2 complex. */
@@ -93,14 +108,19 @@ int mps_statevector(mps_handle_t h, int reg, double* out);
 int mps_measure(mps_handle_t h, int q);
 int mps_clear_measure(mps_handle_t h);
 int mps_seed(mps_handle_t h, uint64_t seed); /* {"seed", int}, TNQVM.hpp:114-117 */
+int mps_n_measured(mps_handle_t h, int* out); /* qubits recorded by mps_measure since the last reset / clear (repeats count) */
 /* finalize() sampling: n < 20 -> GenerateSamples on the state vector (GateMatrixAlgebra.hpp:125-156),
  * n >= 20 -> per-shot sequential RDM sampling (getMeasureSample, ExaTnMpsVisitor.cpp:2211-2364).
- * out: shots * n_measured chars (no terminators); n_out = strings actually produced. */
-int mps_sample(mps_handle_t h, int reg, int shots, char* out, int* n_out);
+ * out: shots * n_measured chars (no terminators), out_cap = its capacity in chars (the call fails when it is smaller than
+ * shots * n_measured); n_out = strings actually produced. */
+int mps_sample(mps_handle_t h, int reg, int shots, char* out, size_t out_cap, int* n_out);
 
 int mps_bond_dims(mps_handle_t h, int* out);                                           /* n_total-1 entries */
 int mps_singular_values(mps_handle_t h, int bond, double* out, int cap, int* count);   /* of the last SVD on that bond */
-int mps_discarded_weight(mps_handle_t h, double* out); /* sum over truncations of discarded/total weight */
+int mps_discarded_weight(mps_handle_t h, double* out); /* sum over truncations of w = discarded/total weight */
+/* fidelity estimate of a truncated run, prod over truncations of (1 - w) (BASELINE config 5; the reference keeps no such record,
+ * ExaTnMpsVisitor.cpp:2366-2536) */
+int mps_fidelity_estimate(mps_handle_t h, double* out);
 int mps_get_site(mps_handle_t h, int k, double* out, int shape[3]);                    /* out may be NULL (shape only) */
 int mps_set_site(mps_handle_t h, int k, const double* in, int dl, int dr);
 
@@ -112,7 +132,9 @@ int mps_resize_site(mps_handle_t h, int k, int dl, int dr, void** dptr);
 /* counters: [0] 2q gates executed, [1] 1q kernel gates, [2] layers, [3] jacobi sweeps, [4] kernel launches,
  * [5] ms merge GEMM, [6] ms SVD (QR pre-reduction + Jacobi), [7] ms truncate+write-back, [8] ms of [6] spent in the QR
  * pre-reduction (5..8 only with option "profile"), [9] real flops issued on the DMMA pipe by the Jacobi pair tasks (process-wide),
- * [10] 2q gates merged into their predecessor on the same site pair (option "fuse_2q") */
+ * [10] 2q gates merged into their predecessor on the same site pair (option "fuse_2q"), [11] SVDs that had not converged
+ * after "jacobi_max_sweeps" sweeps, [12] norm-guard violations, [13] boundary exchanges and [14] bytes moved between devices
+ * (site-sharded handles).  On a sharded handle the counters are sums over the devices. */
 int mps_stats(mps_handle_t h, double* out, int cap);
 /* the CUDA stream (cudaStream_t) all work of this handle is issued on: callers time with events recorded on it
  * and order their own transfers (NCCL send/recv of boundary sites) against it */

@@ -135,8 +135,11 @@ struct Oracle {
   int use_gesdd = 0;
   int gauge = 0;                 // 0 reference (U sqrtS | sqrtS Vh); 1 (U | S Vh); 2 (U S | Vh)
   int renorm = 0;                // never in the reference
+  double null_tol = 0;           // > 0: singular values <= null_tol * sigma_max are rounding noise of an exact zero and are set to 0.0 before the
+                                 // reference's cut rule runs (NOT in the reference: it mirrors the engine's documented deviation)
   std::vector<std::vector<double>> sv;   // last retained singular values per bond
   double discarded = 0;          // accumulated discarded weight (not in reference; diagnostic)
+  double log_fidelity = 0;       // sum of log(1 - w) over truncations: fidelity estimate prod(1 - w) (diagnostic, config 5)
   double t_gemm = 0, t_svd = 0, t_trunc = 0;
   std::mt19937_64 rng;           // RandomEngine.hpp:43 (process-global there; per-handle here)
   std::vector<int> measure;      // visit(Measure) order, ExaTnMpsVisitor.cpp:991-994
@@ -161,6 +164,7 @@ extern "C" Oracle* oracle_create(int n, int max_bond, double svd_cutoff, int cut
 extern "C" void oracle_destroy(Oracle* o) { delete o; }
 extern "C" void oracle_seed(Oracle* o, uint64_t seed) { o->rng.seed(seed); }   // TNQVM.hpp:114-117
 extern "C" void oracle_set_renorm(Oracle* o, int r) { o->renorm = r; }
+extern "C" void oracle_set_null_tol(Oracle* o, double t) { o->null_tol = t; }
 
 // applyGate 1q branch, ExaTnMpsVisitor.cpp:1185-1292: new[b] = sum_i M[b][i] old[i] on the physical leg.
 extern "C" void oracle_apply_1q(Oracle* o, int q, const double* m_ri) {
@@ -241,6 +245,8 @@ extern "C" int oracle_apply_2q(Oracle* o, int q0, int q1, const double* m_ri) {
   if (info != 0) return 3;
   double t2 = now_s();
   o->t_svd += t2 - t1;
+  if (o->null_tol > 0)
+    for (int k = 1; k < r; ++k) if (S[k] <= o->null_tol * S[0]) S[k] = 0.0;
   // truncateSvdTensors (:2366-2536).  Under the reference gauge both partial norms equal
   // sigma_k (sum of squares, comment :2421-2423) or sqrt(sigma_k) (true 2-norm).
   int cut = r;
@@ -251,7 +257,7 @@ extern "C" int oracle_apply_2q(Oracle* o, int q0, int q1, const double* m_ri) {
   const int keep = std::max(1, std::min(cut, o->max_bond));   // :2445
   double tot = 0, kept = 0;
   for (int k = 0; k < r; ++k) { tot += S[k] * S[k]; if (k < keep) kept += S[k] * S[k]; }
-  if (tot > 0) o->discarded += (tot - kept) / tot;
+  if (tot > 0) { const double w = (tot - kept) / tot; o->discarded += w; o->log_fidelity += std::log1p(-std::min(w, 1.0 - 1e-300)); }
   double rn = (o->renorm && kept > 0) ? std::sqrt(tot / kept) : 1.0;
   A.dr = keep; B.dl = keep;
   A.t.assign((size_t)M * keep, 0.0);
@@ -278,6 +284,7 @@ extern "C" int oracle_singular_values(const Oracle* o, int bond, double* out, in
   return (int)v.size();
 }
 extern "C" double oracle_discarded_weight(const Oracle* o) { return o->discarded; }
+extern "C" double oracle_fidelity_estimate(const Oracle* o) { return std::exp(o->log_fidelity); }
 extern "C" void oracle_times(const Oracle* o, double* out3) { out3[0] = o->t_gemm; out3[1] = o->t_svd; out3[2] = o->t_trunc; }
 extern "C" void oracle_get_site(const Oracle* o, int k, double* out_ri, int* shape3) {
   const Site& s = o->s[k];

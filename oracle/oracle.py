@@ -56,12 +56,15 @@ def lib():
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_seed.argtypes = [C.c_void_p, C.c_uint64]
         L.oracle_set_renorm.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_set_null_tol.argtypes = [C.c_void_p, C.c_double]
         L.oracle_apply_1q.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_apply_2q.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_bond_dims.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_singular_values.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_discarded_weight.restype = C.c_double
         L.oracle_discarded_weight.argtypes = [C.c_void_p]
+        L.oracle_fidelity_estimate.restype = C.c_double
+        L.oracle_fidelity_estimate.argtypes = [C.c_void_p]
         L.oracle_times.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_get_site.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_set_site.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
@@ -92,10 +95,12 @@ def gate_matrix(name, params=()):
 class OracleMPS:
     """CPU restatement of ExatnMpsVisitor (reference gauge by default)."""
 
-    def __init__(self, n, max_bond=0, svd_cutoff=-1.0, cutoff_on_sqrt=False, gesdd=False, gauge=0, seed=None):
+    def __init__(self, n, max_bond=0, svd_cutoff=-1.0, cutoff_on_sqrt=False, gesdd=False, gauge=0, seed=None, null_tol=0.0):
         self.L = lib()
         self.n = n
         self.h = self.L.oracle_create(n, int(max_bond), float(svd_cutoff), int(cutoff_on_sqrt), int(gesdd), int(gauge))
+        if null_tol > 0:   # NOT the reference: mirrors the engine's numerically-null rule (DESIGN.md section 1)
+            self.L.oracle_set_null_tol(self.h, float(null_tol))
         if seed is not None:
             self.seed(seed)
 
@@ -151,6 +156,9 @@ class OracleMPS:
 
     def discarded_weight(self):
         return self.L.oracle_discarded_weight(self.h)
+
+    def fidelity_estimate(self):
+        return self.L.oracle_fidelity_estimate(self.h)
 
     def times(self):
         out = np.zeros(3)

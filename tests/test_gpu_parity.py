@@ -162,14 +162,18 @@ def test_config1_truncated_parity(O):
 def test_truncated_parity_within_reference_spread(O, n, depth, chi):
     circ = Cc.brickwork(n, depth, seed=7)
     e = gpu_run(n, circ, max_bond=chi)
-    o = O.OracleMPS(n, max_bond=chi).run(circ)
+    # With the default svd-cutoff (DBL_MIN) the reference rule (ExaTnMpsVisitor.cpp:2434-2443) drops a bond slice only when its
+    # partial norm is an exact floating-point zero, so on rank-deficient thetas the kept dimension depends on whether the SVD
+    # driver returns 0.0 or 1e-17 noise (zgesvd and zgesdd already disagree), and in the reference gauge (sqrt(S) into both
+    # factors, :1623) a noise singular value ~1e-17 leaves ~1e-9 on each neighbour, which the next SVD on an adjacent bond
+    # reports as a "singular value" of that size.  The engine treats numerically-null components as the zeros they stand for
+    # (`null_tol`); the oracle mirrors the rule, and then bond dimensions agree as well.
+    o = O.OracleMPS(n, max_bond=chi, null_tol=10.0 * math.sqrt(2.0 * chi) * 2.220446049250313e-16).run(circ)
     zo = np.array([o.expval_z([k]) for k in range(n)])
     assert np.abs(e.expval_z_all() - zo).max() < TRUNC_TOL
     assert abs(e.norm() - o.norm()) < TRUNC_TOL
-    # With the default svd-cutoff (DBL_MIN) the reference rule (ExaTnMpsVisitor.cpp:2434-2443) drops a bond slice only
-    # when its partial norm is an exact floating-point zero, so on rank-deficient thetas the kept dimension depends on
-    # whether the SVD driver returns 0.0 or 1e-17 noise (zgesvd and zgesdd already disagree).  The slices in question carry
-    # no weight: bond dimensions must agree wherever the singular values are above noise.
+    plain = O.OracleMPS(n, max_bond=chi).run(circ)   # the reference's own rule, noise kept: same observables at this depth
+    assert np.abs(e.expval_z_all() - np.array([plain.expval_z([k]) for k in range(n)])).max() < TRUNC_TOL
     for k, (bg, bo) in enumerate(zip(e.bond_dims(), o.bond_dims())):
         s_g, s_o = e.singular_values(k), o.singular_values(k)
         m = min(len(s_g), len(s_o))
@@ -178,11 +182,7 @@ def test_truncated_parity_within_reference_spread(O, n, depth, chi):
         # arbitrary basis an SVD driver picks inside (near-)degenerate subspaces: the oracle's own zgesvd and zgesdd
         # runs differ by 1.1e-5 relative on this circuit (measured here); observables above agree far tighter
         assert np.abs(s_g[:m] - s_o[:m]).max() < 5e-5 * s_o[0], k
-        # slices only one side keeps must be weightless.  The bound is sqrt(eps)-level, not eps-level: in the reference gauge
-        # (sqrt(S) into both factors, :1623) a rounding-noise singular value sigma ~ 1e-17..1e-20 leaves sqrt(sigma) ~ 1e-9..1e-10
-        # on each neighbour, which the next SVD on an adjacent bond reports as a "singular value" of that size (observed
-        # 1.3e-10 on the oracle side here); the engine zeroes such numerically-null components instead (null_tol).
-        assert (s_g[m:] < 1e-8 * s_o[0]).all() and (s_o[m:] < 1e-8 * s_o[0]).all(), k
+        assert (s_g[m:] < 1e-10 * s_o[0]).all() and (s_o[m:] < 1e-10 * s_o[0]).all(), k   # a borderline null decision at most
     assert abs(e.discarded_weight() - o.discarded_weight()) < 1e-4 * max(1.0, o.discarded_weight())
     e.close()
 
@@ -429,3 +429,264 @@ def test_snapshot_restore_returns_the_exact_state(O):
     o = O.OracleMPS(n, max_bond=chi).run(circ)
     assert np.abs(e.expval_z_all() - np.array([o.expval_z([k]) for k in range(n)])).max() < TRUNC_TOL
     e.close()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# The five BASELINE.json configs at their stated qubit counts, each against the oracle.
+#
+# What can be asserted, measured here first (scripts/parity_diag.py, profiles/r04c_diag.jsonl, r04d_diag.jsonl):
+#  * the per-gate map theta -> (truncated factors) is well conditioned: it is checked gate by gate on the real states of every
+#    config at full qubit count ("teacher-forced": before each dependency layer the engine is loaded with the oracle's
+#    sites, both apply the layer, the new bonds are compared through gauge-invariant quantities);
+#  * the free-running trajectory of a heavily truncated run is NOT: the reference's own algorithm (oracle) run with LAPACK
+#    zgesvd instead of zgesdd ends with norm 0.0191 vs 0.0156 on config 3 (n=100, chi=32), 8.7e-25 vs 2.1e-25 on the real
+#    Sycamore circuit at chi=32, 0.85211 vs 0.85226 on config 2 at full shape -- driver-to-driver differences of 20 %, 4x and
+#    2e-4.  A free-running comparison can therefore only be as tight as the reference agrees with itself;
+#  * the engine drops numerically-null singular components (a documented deviation, engine.cu `null_tol`); the
+#    oracle mirrors that rule through OracleMPS(null_tol=...).  With it mirrored, config 2 at full shape agrees to 1e-13.
+EPS = 2.220446049250313e-16
+
+
+def engine_null_tol(chi):
+    """the engine's automatic numerically-null threshold for thetas of 2 chi rows: 10 x sqrt(rows) x eps"""
+    return 10.0 * math.sqrt(2.0 * chi) * EPS
+
+
+def dependency_layers(n, circ):
+    """the engine's layering (engine.cu flush()): a gate goes one layer after the last gate on any of its qubits"""
+    level, layers = [-1] * n, []
+    for g in circ:
+        if g[0] in ("Measure", "I"):
+            continue
+        l = max(level[q] for q in g[1]) + 1
+        if len(layers) <= l:
+            layers.append([])
+        layers[l].append(g)
+        for q in g[1]:
+            level[q] = l
+    return layers
+
+
+def teacher_forced_parity(O, n, circ, chi, layer_pick=lambda i: True, tol=1e-10):
+    """Oracle (engine's null rule mirrored) runs `circ`; for every picked dependency layer the engine gets the oracle's sites of
+    the qubits the layer touches, applies the same layer, and every 2q gate is checked on its new bond:
+      (1) kept bond dimension and kept singular values equal the oracle's;
+      (2) the product of the two new sites is an OPTIMAL rank-keep approximation of theta (theta built here from the oracle's
+          sites before the layer): its residual equals sqrt(sum of the discarded sigma^2) -- valid even when max-bond-dim cuts
+          through a degenerate multiplet, where the kept subspace itself is not unique;
+      (3) where the cut is non-degenerate, the product equals the oracle's.
+    Returns (gates checked, gates with a degenerate cut, worst deviations)."""
+    o = O.OracleMPS(n, max_bond=chi, gesdd=True, null_tol=engine_null_tol(chi))
+    e = tnqvm_b200.B200MPS(n, max_bond=chi)
+    worst = dict(dsigma=0.0, dresid=0.0, dprod=0.0)
+    checked = degenerate = mismatched = 0
+    for li, layer in enumerate(dependency_layers(n, circ)):
+        if not layer_pick(li):
+            for g in layer:
+                o.apply(g[0], g[1], g[2])
+            continue
+        touched = sorted({q for g in layer for q in g[1]})
+        pre = {q: o.get_site(q) for q in touched}
+        for q in touched:
+            e.set_site(q, pre[q])
+        for g in layer:
+            o.apply(g[0], g[1], g[2])
+            e.apply(g[0], g[1], g[2])
+        e.flush()
+        for g in layer:
+            if len(g[1]) != 2:
+                continue
+            lo = min(g[1])
+            m = tnqvm_b200.gates.gate_matrix(g[0], g[2]).reshape(2, 2, 2, 2)
+            if g[1][0] > g[1][1]:
+                m = m.transpose(1, 0, 3, 2)
+            th = np.einsum('pqij,aijc->apqc', m, np.einsum('apk,kqc->apqc', pre[lo], pre[lo + 1]))
+            a, _, _, c = th.shape
+            th = th.reshape(2 * a, 2 * c)
+            sv = np.linalg.svd(th, compute_uv=False)
+            Ae, Be, Ao, Bo = e.get_site(lo), e.get_site(lo + 1), o.get_site(lo), o.get_site(lo + 1)
+            keep = Ae.shape[2]
+            s_e, s_o = e.singular_values(lo), o.singular_values(lo)
+            mk = min(len(s_e), len(s_o))
+            # the kept dimension may differ by borderline numerically-null decisions only (sigma within 1000x of the threshold)
+            assert Ae.shape[0] == Ao.shape[0] and Be.shape[2] == Bo.shape[2], (li, g)
+            assert (s_e[mk:] < 1e-10 * sv[0]).all() and (s_o[mk:] < 1e-10 * sv[0]).all(), (li, g, len(s_e), len(s_o))
+            mismatched += int(len(s_e) != len(s_o))
+            ds = np.abs(s_e[:mk] - s_o[:mk]).max() / sv[0]
+            Pe = np.einsum('apk,kqc->apqc', Ae, Be).reshape(2 * a, 2 * c)
+            Po = np.einsum('apk,kqc->apqc', Ao, Bo).reshape(2 * a, 2 * c)
+            best = math.sqrt(float((sv[keep:] ** 2).sum()))
+            dr = abs(np.linalg.norm(th - Pe) - best) / sv[0]
+            worst["dsigma"] = max(worst["dsigma"], ds); worst["dresid"] = max(worst["dresid"], dr)
+            assert ds < tol, (li, g, ds)
+            assert dr < 10 * tol, (li, g, dr)
+            ko = Ao.shape[2]
+            kk = max(keep, ko)
+            gap = (sv[min(keep, ko) - 1] - sv[kk]) / sv[0] if kk < len(sv) else 1.0
+            if gap > 1e-9:   # subspace perturbation ~ rounding / gap
+                dp = np.abs(Pe - Po).max() / sv[0]
+                worst["dprod"] = max(worst["dprod"], dp)
+                assert dp < max(tol, 1e-13 / gap), (li, g, dp, gap)
+            else:
+                degenerate += 1
+            checked += 1
+    e.close()
+    worst["kept_dim_differs"] = mismatched
+    return checked, degenerate, worst
+
+
+def test_config2_full_shape_parity(O):
+    """BASELINE config 2 as stated: 50-qubit brickwork depth 20, max-bond-dim 256, seed 12345 (the circuit bench.py times),
+    free-running GPU vs the oracle with the engine's numerically-null rule mirrored: <Z_k> for all k, norm, bond dimensions,
+    discarded weight, fidelity estimate.  (Against the plain-LAPACK oracle the norm differs by 4e-4 -- the oracle's own zgesvd
+    and zgesdd runs differ by 2e-4; that comparison is recorded in profiles/r04d_diag.jsonl.)"""
+    n, depth, chi = 50, 20, 256
+    circ = Cc.brickwork(n, depth, seed=12345)
+    e = gpu_run(n, circ, max_bond=chi)
+    z, nrm, bonds, dw, fid = e.expval_z_all(), e.norm(), e.bond_dims(), e.discarded_weight(), e.fidelity_estimate()
+    assert e.stats()["svd_nonconverged"] == 0
+    e.close()
+    O.lib().oracle_set_threads(os.cpu_count() or 1)
+    o = O.OracleMPS(n, max_bond=chi, gesdd=True, null_tol=engine_null_tol(chi)).run(circ)
+    zo = np.array([o.expval_z([k]) for k in range(n)])
+    assert (np.asarray(bonds) == np.asarray(o.bond_dims())).all()
+    assert abs(nrm - o.norm()) < TRUNC_TOL, (nrm, o.norm())
+    assert np.abs(z - zo).max() < TRUNC_TOL, np.abs(z - zo).max()
+    assert abs(dw - o.discarded_weight()) < 1e-6 * max(1.0, o.discarded_weight())
+    assert abs(fid - o.fidelity_estimate()) < 1e-6
+
+
+def test_config2_full_shape_teacher_forced(O):
+    """Config 2 at full shape, gate by gate on the oracle's own states (every third dependency layer: 512x512 LAPACK SVDs on
+    the host set the cost)."""
+    n, depth, chi = 50, 20, 256
+    O.lib().oracle_set_threads(os.cpu_count() or 1)
+    checked, degenerate, worst = teacher_forced_parity(O, n, Cc.brickwork(n, depth, seed=12345), chi, layer_pick=lambda i: i % 3 == 1)
+    assert checked >= 150 and degenerate == 0 and worst["kept_dim_differs"] == 0, (checked, degenerate, worst)
+
+
+def test_config3_full_qubit_count_teacher_forced(O):
+    """BASELINE config 3 at its stated 100 qubits and p = 4 (ring MaxCut QAOA, the wrap edge routed by the nearest-neighbour
+    pass: 2368 NN 2q gates in ~800 dependency layers) with a max-bond-dim the oracle finishes in seconds, every gate of every
+    layer checked.  QAOA states carry exactly degenerate Schmidt multiplets, so max-bond-dim often cuts through one: there
+    the kept subspace is arbitrary and only the singular values and the optimality of the truncation are comparable."""
+    n, p, chi = 100, 4, 32
+    circ = Cc.nearest_neighbor(Cc.qaoa_ring(n, p, seed=7))
+    assert Cc.count_gates(circ)[1] == 2368
+    checked, degenerate, worst = teacher_forced_parity(O, n, circ, chi)
+    assert checked == 2368 and worst["kept_dim_differs"] < 0.05 * checked, (checked, degenerate, worst)
+
+
+def test_config3_full_qubit_count_observables_untruncated_prefix(O):
+    """Config 3 observables at 100 qubits where the reference is reproducible: the first QAOA layer (p = 1) keeps every bond
+    below max-bond-dim 32 except along the routed wrap edge, so nothing is cut through a multiplet and the free-running run
+    must match the oracle: <Z_i Z_j> on all 100 ring edges, the cut energy and the norm."""
+    n, chi = 100, 64
+    circ = Cc.nearest_neighbor(Cc.qaoa_ring(n, 1, seed=7))
+    edges = [(i, (i + 1) % n) for i in range(n)]
+    e = tnqvm_b200.B200MPS(n, max_bond=chi)
+    e.run(circ)
+    zz, nrm = e.expval_zz_pairs(edges), e.norm()
+    e.close()
+    o = O.OracleMPS(n, max_bond=chi, gesdd=True, null_tol=engine_null_tol(chi)).run(circ)
+    ref = np.array([o.expval_z([i, j]) for i, j in edges])
+    assert abs(nrm - o.norm()) < TRUNC_TOL, (nrm, o.norm())
+    assert np.abs(zz - ref).max() < TRUNC_TOL
+    assert abs(((nrm - zz) / 2).sum() - ((o.norm() - ref) / 2).sum()) < n * TRUNC_TOL
+
+
+def test_config4_hea64_64_parameter_sets(O):
+    """BASELINE config 4 as stated: 64-qubit hardware-efficient ansatz (4 layers of Ry, Rz + CX ladder), 64 parameter sets
+    (seeds 0..63) as 64 registers of one handle, max-bond-dim 64, <Z_k> for every qubit of every set against the oracle."""
+    n, R, chi = 64, 64, 64
+    eb = tnqvm_b200.B200MPS(n, n_registers=R, max_bond=chi)
+    circs = [Cc.hea(n, 4, seed=s) for s in range(R)]
+    for r, c in enumerate(circs):
+        eb.run(c, offset=r * n)
+    for r, c in enumerate(circs):
+        o = O.OracleMPS(n, max_bond=chi).run(c)
+        zo = np.array([o.expval_z([k]) for k in range(n)])
+        assert np.abs(eb.expval_z_all(reg=r) - zo).max() < EXACT_TOL, r   # bonds stay <= 16: no truncation happens
+        assert abs(eb.norm(reg=r) - o.norm()) < EXACT_TOL
+    eb.close()
+
+
+def test_config5_real_sycamore_53_depth14_teacher_forced(O):
+    """BASELINE config 5 on the circuit it names: examples/sycamore/resources/sycamore_53_14_0.xasm (committed as a data
+    fixture, tests/golden/make_sycamore_fixture.py), routed by the nearest-neighbour pass into 1897 NN 2q gates; every gate
+    checked on the oracle's own states at max-bond-dim 64."""
+    n, raw = Cc.sycamore_53(14)
+    circ = Cc.nearest_neighbor(raw)
+    assert n == 53 and Cc.count_gates(circ) == (2527, 1897)
+    O.lib().oracle_set_threads(os.cpu_count() or 1)
+    checked, degenerate, worst = teacher_forced_parity(O, n, circ, 64)
+    assert checked == 1897 and worst["kept_dim_differs"] < 0.05 * checked, (checked, degenerate, worst)
+
+
+def test_config5_real_sycamore_outputs_within_reference_reproducibility(O):
+    """The outputs of the reference's Sycamore driver (examples/sycamore/sycamore_circ_mps.cpp:42-47) plus the fidelity estimate
+    prod(1 - w), free-running at max-bond-dim 32.  The run discards almost everything (norm ~ 1e-25) and the trajectory is
+    chaotic: the oracle's own zgesvd and zgesdd runs differ by a factor of 4 in the norm.  Asserted: the engine lies within the
+    reference's own reproducibility (a decade), bond dimensions and the summed discarded weight agree to a few percent."""
+    n, raw = Cc.sycamore_53(14)
+    circ = Cc.nearest_neighbor(raw)
+    chi = 32
+    e = tnqvm_b200.B200MPS(n, max_bond=chi)
+    e.run(circ)
+    nrm, amp, fid, dw, bonds = e.norm(), e.amplitude([0] * n), e.fidelity_estimate(), e.discarded_weight(), e.bond_dims()
+    assert e.stats()["svd_nonconverged"] == 0
+    e.close()
+    runs = [O.OracleMPS(n, max_bond=chi, gesdd=dd, null_tol=nt).run(circ) for dd in (False, True) for nt in (0.0, engine_null_tol(chi))]
+    norms = np.array([o.norm() for o in runs])
+    assert norms.min() / 10 < nrm < norms.max() * 10, (nrm, norms)
+    assert abs(amp) ** 2 < 1e3 * norms.max()
+    dws = np.array([o.discarded_weight() for o in runs])
+    assert abs(dw - dws.mean()) < 0.05 * dws.mean(), (dw, dws)
+    assert abs(int(np.sum(bonds)) - int(np.sum(runs[-1].bond_dims()))) <= 0.02 * np.sum(bonds)   # borderline null decisions only
+    assert 0.0 <= fid < 1e-20 and all(0.0 <= o.fidelity_estimate() < 1e-20 for o in runs)
+
+
+@pytest.mark.parametrize("devices,partition_by", [([0, 0], "cost"), ([0, 0, 0], "count"), ("all", "cost")])
+def test_site_sharded_handle_matches_single_engine(O, devices, partition_by):
+    """mps_create_sharded (the MPI site blocks of ExaTnMpsVisitor.cpp:347-531 / :2059-2170 as one process driving several
+    engines): same circuit on a sharded handle and on one engine -- <Z_k>, <Z_i Z_j>, norm, amplitudes, bond dimensions, bond
+    spectra, samples, snapshot/restore -- and both against the oracle.  [0, 0] puts two blocks on one GPU, which runs the whole
+    exchange logic (worker threads, events, copies) on a single-GPU box; "all" uses every GPU present."""
+    import torch
+    if devices == "all":
+        devices = list(range(torch.cuda.device_count()))
+        if len(devices) < 2:
+            pytest.skip("needs at least 2 GPUs")
+    n, chi = 18, 16
+    circ = Cc.nearest_neighbor(Cc.brickwork(n, 8, seed=5, prefix_ghz=True) + [("fSim", (2, 11), (0.4, 0.7)), ("CNOT", (9, 8), ()), ("Swap", (8, 9), ())])
+    a = tnqvm_b200.B200MPS(n, max_bond=chi, seed=3)
+    b = tnqvm_b200.B200MPS(n, max_bond=chi, seed=3, devices=devices, partition_by=partition_by)
+    lay = b.shard_layout()
+    assert len(lay) == len(devices) + 1 and lay[0] == 0 and lay[-1] == n and all(x < y for x, y in zip(lay, lay[1:]))
+    a.run(circ); b.run(circ)
+    assert b.stats()["boundary_exchanges"] > 0 and b.stats()["peer_bytes"] > 0
+    assert (a.bond_dims() == b.bond_dims()).all()
+    assert np.abs(a.expval_z_all() - b.expval_z_all()).max() < 1e-12
+    assert abs(a.norm() - b.norm()) < 1e-12
+    pairs = [(0, 1), (lay[1] - 1, lay[1]), (3, n - 1)]
+    assert np.abs(a.expval_zz_pairs(pairs) - b.expval_zz_pairs(pairs)).max() < 1e-12
+    bits = [k % 2 for k in range(n)]
+    assert abs(a.amplitude(bits) - b.amplitude(bits)) < 1e-12
+    for k in (0, lay[1] - 1, lay[1], n - 2):
+        assert np.abs(a.singular_values(k) - b.singular_values(k)).max() < 1e-12
+    assert abs(a.discarded_weight() - b.discarded_weight()) < 1e-12
+    o = O.OracleMPS(n, max_bond=chi, null_tol=engine_null_tol(chi)).run(circ)
+    assert np.abs(b.expval_z_all() - np.array([o.expval_z([k]) for k in range(n)])).max() < TRUNC_TOL
+    # snapshot / restore and more gates on the sharded handle
+    b.snapshot(); a.snapshot()
+    more = Cc.brickwork(n, 3, seed=9)
+    a.run(more); b.run(more)
+    assert np.abs(a.expval_z_all() - b.expval_z_all()).max() < 1e-12
+    a.restore(); b.restore()
+    assert np.abs(a.expval_z_all() - b.expval_z_all()).max() < 1e-12
+    for q in (4, 0, n - 1):
+        a.measure(q); b.measure(q)
+    assert a.sample_strings(50, 3) == b.sample_strings(50, 3)
+    b.reset()
+    assert abs(b.norm() - 1.0) < 1e-14 and (b.bond_dims() == 1).all()
+    a.close(); b.close()

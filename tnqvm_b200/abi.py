@@ -16,6 +16,8 @@ def lib_path():
 
 SYMBOLS = {
     "mps_create": ([C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)], C.c_int),
+    "mps_create_sharded": ([C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)], C.c_int),
+    "mps_shard_layout": ([C.c_void_p, C.POINTER(C.c_int), C.c_void_p], C.c_int),
     "mps_destroy": ([C.c_void_p], C.c_int),
     "mps_last_error": ([C.c_void_p], C.c_char_p),
     "mps_reset": ([C.c_void_p], C.c_int),
@@ -37,10 +39,12 @@ SYMBOLS = {
     "mps_measure": ([C.c_void_p, C.c_int], C.c_int),
     "mps_clear_measure": ([C.c_void_p], C.c_int),
     "mps_seed": ([C.c_void_p, C.c_uint64], C.c_int),
-    "mps_sample": ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)], C.c_int),
+    "mps_n_measured": ([C.c_void_p, C.POINTER(C.c_int)], C.c_int),
+    "mps_sample": ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)], C.c_int),
     "mps_bond_dims": ([C.c_void_p, C.c_void_p], C.c_int),
     "mps_singular_values": ([C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)], C.c_int),
     "mps_discarded_weight": ([C.c_void_p, C.POINTER(C.c_double)], C.c_int),
+    "mps_fidelity_estimate": ([C.c_void_p, C.POINTER(C.c_double)], C.c_int),
     "mps_get_site": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
     "mps_set_site": ([C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int], C.c_int),
     "mps_site_device_ptr": ([C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p], C.c_int),

@@ -8,6 +8,11 @@
 // The only host synchronisation per layer is the read-back of the kept bond dimensions.
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -74,15 +79,50 @@ static void segv_handler(int sig) {
   _exit(128 + sig);
 }
 
+// ---- sites sharded over the devices of one box (replaces the MPI site blocks of ExaTnMpsVisitor.cpp:347-531 and
+// the boundary dispatch of :2059-2170).  One host process, one engine (sub-handle) and one worker thread per device.
+// A boundary site travels as ONE peer copy over NVLink each way (32 chi^2 bytes); nothing else moves.
+struct XferSlot {
+  std::mutex mu;
+  std::condition_variable cv;
+  bool ready = false;
+  const double2* ptr = nullptr;
+  int dl = 0, dr = 0, src_dev = 0;
+  cudaEvent_t ev = nullptr;   // recorded on the sender's stream behind the work that produced the tensor
+};
+struct ShardOp {
+  enum Kind { LAYER, SEND, RECV } kind;
+  int site = -1, slot = -1;
+  std::vector<int> gates;   // LAYER: indices into the coordinator's queue
+};
+struct ShardGroup {
+  std::vector<mps_b200_handle*> sub;           // one engine per device; sub[d] owns the sites [bounds[d].first, bounds[d].second)
+  std::vector<std::pair<int, int>> bounds;
+  std::vector<int> owner;                      // per site
+  std::deque<XferSlot> slots;
+  std::atomic<bool> abort{false};
+  std::mutex err_mu;
+  std::string first_error;
+  double exchanges = 0, bytes_moved = 0;
+  int gathered_ver = -1;                       // state version of the copy of all sites held by sub[0] (observables, v1)
+};
+
 }  // namespace
 
 struct mps_b200_handle {
+  ShardGroup* grp = nullptr;   // non-null: this handle is the coordinator of a site-sharded group and owns no device state
+  std::vector<cudaEvent_t> xev;   // sub-handle of a group: events of its outgoing boundary transfers (reused across flushes)
+  size_t xev_used = 0;
   int nq = 0, nreg = 1, ntot = 0;
   int max_bond = INT_MAX - 1;
   double cutoff = DBL_MIN;
   int gauge = 0, device = 0;
   int cutoff_on_sqrt = 0, fuse_1q = 1, renorm = 0, profile = 0, layer_batch = 1, use_qr = 1;
-  int norm_guard = 1;   // post-SVD sanity check of ExaTnMpsVisitor.cpp:1632-1661 (both factors must have 2-norm >= 1e-3)
+  // post-SVD sanity check of ExaTnMpsVisitor.cpp:1632-1661 (both factors must have 2-norm >= 1e-3).  The reference prints
+  // "[ERROR] Tensor norm validation failed!" and asserts, i.e. it crashes in Debug builds and carries on in Release builds (its
+  // default, CMakeLists.txt:52-56).  2 (default) = Release behaviour: one line on stderr per handle, counted in mps_stats[12];
+  // 1 = Debug behaviour: the call fails; 0 = off.
+  int norm_guard = 2;
   // fuse_2q: consecutive 2q gates on the same site pair (and the 1q gates between them) become one 4x4 before they reach
   // the GPU, e.g. CX.Rz.CX = ZZ(gamma) of the QAOA circuits or Swap.Swap = 1 between two routed gates.
   // Off by default: the reference truncates after every 2q gate (ExaTnMpsVisitor.cpp:1394-1630), so with truncation
@@ -91,14 +131,22 @@ struct mps_b200_handle {
   std::vector<int> last_touch;   // per site: index in `queue` of the last queued gate on it (-1: none since the flush)
   double nfused2q = 0;
   double jacobi_tol = 0.0;   // 0 -> sqrt(M) * eps
-  double null_tol = 0.0;     // 0 -> 10 * jacobi tolerance
+  // Numerically-null components: sigma_k <= null_tol * sigma_max (<= 0: automatic, 10 x the Jacobi tolerance) is rounding noise
+  // of an exact zero.  Such columns are not rotated by the Jacobi sweeps and both factors of the component are zeroed at
+  // write-back.  This is a DOCUMENTED DEVIATION from the reference, where LAPACK inside ExaTN returns noise singular values
+  // (~1e-17 sigma_max) with arbitrary orthonormal vectors for rank-deficient thetas and the cut rule of :2434-2443 only drops
+  // exact zeros; in the sqrt(S) gauge that noise grows by a square root per SVD until it competes with real weight for the
+  // max-bond-dim slots (DESIGN.md section 1 quantifies it).  The engine cannot reproduce LAPACK's noise vectors (the second
+  // factor comes from theta * G / sigma^2, which amplifies noise columns), so there is no "keep" mode; the CPU checker of
+  // the test-suite mirrors this rule through an option of its own so that parity can be checked like for like.
+  double null_tol = 0.0;
   int max_sweeps = 40;
   cudaStream_t stream = nullptr;
   std::vector<SiteBuf> sites;
   // VQE mode: the ansatz state every observable term starts from (mps_snapshot / mps_restore)
   std::vector<SiteBuf> snap;
   std::vector<std::vector<double>> snap_sv;
-  double snap_discarded = 0.0;
+  double snap_discarded = 0.0, snap_log_fidelity = 0.0;
   bool has_snap = false;
   std::vector<char> has1q;
   std::vector<std::array<cplx, 4>> p1q;
@@ -107,6 +155,7 @@ struct mps_b200_handle {
   std::vector<int> measure;
   std::mt19937_64 rng;
   double discarded = 0.0;
+  double log_fidelity = 0.0;   // sum over truncations of log(1 - discarded/total): the fidelity estimate prod(1 - w) of config 5
   std::string err;
   // <psi|psi> of a register is remembered until its state changes (expval_z_all computes it on the way)
   uint64_t state_ver = 1;
@@ -199,6 +248,7 @@ struct mps_b200_handle {
     std::fill(has1q.begin(), has1q.end(), 0);
     measure.clear();
     discarded = 0.0;
+    log_fidelity = 0.0;
     const cplx zero_state[2] = {cplx(1, 0), cplx(0, 0)};
     for (int k = 0; k < ntot; ++k) {
       ensure_site(k, 1, 1, false);
@@ -226,6 +276,7 @@ struct mps_b200_handle {
     }
     snap_sv = sv;
     snap_discarded = discarded;
+    snap_log_fidelity = log_fidelity;
     has_snap = true;
   }
   void restore_state() {
@@ -239,6 +290,7 @@ struct mps_b200_handle {
     }
     sv = snap_sv;
     discarded = snap_discarded;
+    log_fidelity = snap_log_fidelity;
   }
 
   int reg_of(int q) const { return q / nq; }
@@ -313,7 +365,9 @@ struct mps_b200_handle {
     if (!layer_batch) flush();
   }
 
+  void group_flush();   // defined below the struct
   void flush() {
+    if (grp) { group_flush(); return; }
     if (!queue.empty() || std::find(has1q.begin(), has1q.end(), (char)1) != has1q.end()) ++state_ver;
     if (!queue.empty()) {
       // dependency layering: a gate goes one layer after the last gate touching any of its sites
@@ -681,14 +735,21 @@ struct mps_b200_handle {
           n_hi += (gauge == 0) ? s : (gauge == 1 ? s * s : 1.0);
         }
         if (std::sqrt(n_lo) < 1e-3 || std::sqrt(n_hi) < 1e-3) {
+          if (guard_violations == 0 && norm_guard == 2)
+            fprintf(stderr, "[ERROR] Tensor norm validation failed! sites (%d,%d): ||Q_lo|| = %g, ||Q_hi|| = %g (ExaTnMpsVisitor.cpp:1632-1661; reported once per handle)\n",
+                    d.lo, d.lo + 1, std::sqrt(n_lo), std::sqrt(n_hi));
           guard_violations += 1;
           if (norm_guard == 1)
             throw std::runtime_error("tensor norm validation failed after the SVD on sites (" + std::to_string(d.lo) + "," + std::to_string(d.lo + 1) +
                                      "): ||Q_lo|| = " + std::to_string(std::sqrt(n_lo)) + ", ||Q_hi|| = " + std::to_string(std::sqrt(n_hi)) +
-                                     " (ExaTnMpsVisitor.cpp:1632-1661; option norm_guard = 2 counts instead of failing)");
+                                     " (ExaTnMpsVisitor.cpp:1632-1661; option norm_guard = 1 is the Debug-build behaviour)");
         }
       }
-      if (h_w[2 * b] > 0) discarded += (h_w[2 * b] - h_w[2 * b + 1]) / h_w[2 * b];
+      if (h_w[2 * b] > 0) {
+        const double w = (h_w[2 * b] - h_w[2 * b + 1]) / h_w[2 * b];
+        discarded += w;
+        log_fidelity += std::log1p(-std::min(w, 1.0 - 1e-300));
+      }
       sv[d.lo].assign(h_sig + so, h_sig + so + keep);
       so += d.Ng;
       ensure_site(d.lo, d.cl, keep, false);
@@ -977,6 +1038,217 @@ struct mps_b200_handle {
   }
 };
 
+
+// =================================================================================== site-sharded group
+namespace {
+
+// Contiguous site blocks per device.  by_cost: blocks of equal estimated SVD cost M N min(M, N) on the saturated bond profile
+// min(max_bond, 2^k, 2^(n-k)) ("partition by sum chi^3, not by site count"; a gate on bond k is charged to the owner
+// of site k, which executes it); otherwise equal counts.  One formula (the reference's two disagree when n % P != 0).
+std::vector<std::pair<int, int>> shard_partition(int n, int world, int max_bond, bool by_cost) {
+  std::vector<std::pair<int, int>> out;
+  if (world < 1 || n < world) throw std::runtime_error("need at least one site per device");
+  if (!by_cost || max_bond <= 0 || max_bond >= (1 << 20) || world == 1) {
+    int s = 0;
+    for (int r = 0; r < world; ++r) {
+      const int e = s + n / world + (r < n % world ? 1 : 0);
+      out.push_back({s, e});
+      s = e;
+    }
+    return out;
+  }
+  std::vector<double> dims(n + 1, 1.0), w(n, 0.0);
+  for (int k = 0; k + 1 < n; ++k) dims[k + 1] = std::min<double>(max_bond, std::ldexp(1.0, std::min({k + 1, n - 1 - k, 60})));
+  double total = 0;
+  for (int k = 0; k + 1 < n; ++k) {
+    const double m = 2.0 * dims[k], nn = 2.0 * dims[k + 2];
+    w[k] = m * nn * std::min(m, nn);
+    total += w[k];
+  }
+  int s = 0;
+  double acc = 0;
+  for (int r = 0; r < world; ++r) {
+    int e;
+    if (r == world - 1) e = n;
+    else {
+      e = s + 1;
+      acc += w[s];
+      const double target = total * (r + 1) / world;
+      while (e < n - (world - 1 - r) && std::fabs(acc + w[e] - target) <= std::fabs(acc - target)) { acc += w[e]; ++e; }
+    }
+    out.push_back({s, e});
+    s = e;
+  }
+  return out;
+}
+
+}  // namespace
+
+// Executes the coordinator's queue on the group.  The queue is cut into dependency layers exactly as on one device; a device
+// runs, per layer, the gates whose LEFT site it owns as one batched run_layer.  For a gate on a block boundary the right
+// owner publishes its boundary site before that layer (SEND), the left owner copies it over NVLink (RECV: one
+// cudaMemcpyPeerAsync ordered by an event, no host synchronisation), runs the gate with the rest of its layer and publishes the
+// new tensor (SEND); the right owner takes it back only when one of its own later gates touches that site.  All devices
+// therefore execute a brickwork layer concurrently; the only waits are on tensors that really cross a boundary.
+void mps_b200_handle::group_flush() {
+  ShardGroup& G = *grp;
+  const int P = (int)G.sub.size();
+  // leftover folded 1q gates become queue entries (last in program order)
+  for (int q = 0; q < ntot; ++q)
+    if (has1q[q]) {
+      QGate g;
+      g.q0 = q; g.q1 = -1;
+      for (int i = 0; i < 4; ++i) g.m[i] = p1q[q][i];
+      queue.push_back(g);
+      has1q[q] = 0;
+    }
+  if (queue.empty()) return;
+  ++state_ver;
+  std::vector<int> level(ntot, -1);
+  std::vector<std::vector<int>> layers;
+  for (size_t i = 0; i < queue.size(); ++i) {
+    const QGate& g = queue[i];
+    if (g.skip) continue;
+    int l = level[g.q0];
+    if (g.q1 >= 0) l = std::max(l, level[g.q1]);
+    ++l;
+    if ((int)layers.size() <= l) layers.resize(l + 1);
+    layers[l].push_back((int)i);
+    level[g.q0] = l;
+    if (g.q1 >= 0) level[g.q1] = l;
+  }
+  // per-device op lists
+  std::vector<std::vector<ShardOp>> ops(P);
+  std::vector<int> away(ntot, -1);   // site k is on its left neighbour's device; slot of its way back (-1: at home)
+  G.slots.clear();
+  auto new_slot = [&]() { G.slots.emplace_back(); return (int)G.slots.size() - 1; };
+  auto op = [](ShardOp::Kind k, int site, int slot) { ShardOp o; o.kind = k; o.site = site; o.slot = slot; return o; };
+  for (auto& L : layers) {
+    std::vector<std::vector<ShardOp>> back(P), send(P), recv(P), post(P);
+    std::vector<ShardOp> run(P);
+    for (int d = 0; d < P; ++d) run[d].kind = ShardOp::LAYER;
+    for (int gi : L) {
+      const QGate& g = queue[gi];
+      const int lo = g.q1 < 0 ? g.q0 : std::min(g.q0, g.q1), hi = g.q1 < 0 ? g.q0 : std::max(g.q0, g.q1);
+      const int A = G.owner[lo], B = G.owner[hi];
+      for (int k : {lo, hi})
+        if (away[k] >= 0) { back[G.owner[k]].push_back(op(ShardOp::RECV, k, away[k])); away[k] = -1; }
+      if (A != B) {
+        const int s1 = new_slot(), s2 = new_slot();
+        send[B].push_back(op(ShardOp::SEND, hi, s1));
+        recv[A].push_back(op(ShardOp::RECV, hi, s1));
+        post[A].push_back(op(ShardOp::SEND, hi, s2));
+        away[hi] = s2;
+        G.exchanges += 1;
+      }
+      run[A].gates.push_back(gi);
+    }
+    for (int d = 0; d < P; ++d) {
+      for (auto* v : {&back[d], &send[d], &recv[d]}) ops[d].insert(ops[d].end(), v->begin(), v->end());
+      if (!run[d].gates.empty()) ops[d].push_back(run[d]);
+      ops[d].insert(ops[d].end(), post[d].begin(), post[d].end());
+    }
+  }
+  for (int k = 0; k < ntot; ++k)
+    if (away[k] >= 0) ops[G.owner[k]].push_back(op(ShardOp::RECV, k, away[k]));   // every site is home when the flush returns
+
+  G.abort = false;
+  G.first_error.clear();
+  auto worker = [&](int d) {
+    mps_b200_handle* S = G.sub[d];
+    try {
+      CK(cudaSetDevice(S->device));
+      S->xev_used = 0;
+      for (const ShardOp& o : ops[d]) {
+        if (G.abort) break;
+        if (o.kind == ShardOp::LAYER) {
+          S->queue.clear();
+          std::vector<int> idx;
+          for (int gi : o.gates) { idx.push_back((int)S->queue.size()); S->queue.push_back(queue[gi]); }
+          ++S->state_ver;
+          S->run_layer(idx);
+          S->queue.clear();
+        } else if (o.kind == ShardOp::SEND) {
+          if (S->xev_used == S->xev.size()) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            S->xev.push_back(e);
+          }
+          cudaEvent_t e = S->xev[S->xev_used++];
+          CK(cudaEventRecord(e, S->stream));
+          XferSlot& x = G.slots[o.slot];
+          {
+            std::lock_guard<std::mutex> lk(x.mu);
+            x.ptr = S->sites[o.site].d; x.dl = S->sites[o.site].dl; x.dr = S->sites[o.site].dr; x.src_dev = S->device; x.ev = e;
+            x.ready = true;
+          }
+          x.cv.notify_all();
+        } else {
+          XferSlot& x = G.slots[o.slot];
+          {
+            std::unique_lock<std::mutex> lk(x.mu);
+            x.cv.wait(lk, [&] { return x.ready || G.abort.load(); });
+            if (!x.ready) break;
+          }
+          // order: wait for the producer, THEN (re)allocate -- the buffer this replaces may still be read by the peer's
+          // previous copy, which lies before the producer's event in the peer's stream
+          CK(cudaStreamWaitEvent(S->stream, x.ev, 0));
+          S->ensure_site(o.site, x.dl, x.dr, false);
+          const size_t bytes = (size_t)2 * x.dl * x.dr * sizeof(double2);
+          CK(cudaMemcpyPeerAsync(S->sites[o.site].d, S->device, x.ptr, x.src_dev, bytes, S->stream));
+          ++S->state_ver;
+          std::lock_guard<std::mutex> lk(G.err_mu);
+          G.bytes_moved += (double)bytes;
+        }
+      }
+      CK(cudaGetLastError());
+    } catch (const std::exception& e) {
+      {
+        std::lock_guard<std::mutex> lk(G.err_mu);
+        if (G.first_error.empty()) G.first_error = "device " + std::to_string(S->device) + ": " + e.what();
+      }
+      G.abort = true;
+      for (auto& x : G.slots) { std::lock_guard<std::mutex> lk(x.mu); x.cv.notify_all(); }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int d = 1; d < P; ++d) th.emplace_back(worker, d);
+  worker(0);
+  for (auto& t : th) t.join();
+  queue.clear();
+  std::fill(last_touch.begin(), last_touch.end(), -1);
+  CK(cudaSetDevice(device));
+  if (!G.first_error.empty()) throw std::runtime_error(G.first_error);
+}
+
+namespace {
+// v1 of the group observables: every site is copied to device 0 (peer copies, ordered by events) and sub[0] evaluates.
+mps_b200_handle* group_gather(mps_b200_handle* h) {
+  ShardGroup& G = *h->grp;
+  h->flush();
+  mps_b200_handle* S0 = G.sub[0];
+  if (G.gathered_ver == (int)(h->state_ver & 0x7fffffff)) return S0;
+  for (size_t d = 1; d < G.sub.size(); ++d) {
+    mps_b200_handle* S = G.sub[d];
+    CK(cudaSetDevice(S->device));
+    if (S->xev.empty()) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); S->xev.push_back(e); }
+    CK(cudaEventRecord(S->xev[0], S->stream));
+    CK(cudaSetDevice(S0->device));
+    CK(cudaStreamWaitEvent(S0->stream, S->xev[0], 0));
+    for (int k = G.bounds[d].first; k < G.bounds[d].second; ++k) {
+      const SiteBuf& src = S->sites[k];
+      S0->ensure_site(k, src.dl, src.dr, false);
+      CK(cudaMemcpyPeerAsync(S0->sites[k].d, S0->device, src.d, S->device, (size_t)2 * src.dl * src.dr * sizeof(double2), S0->stream));
+    }
+  }
+  CK(cudaSetDevice(S0->device));
+  CK(cudaStreamSynchronize(S0->stream));   // the owners may change their sites as soon as this returns
+  ++S0->state_ver;
+  G.gathered_ver = (int)(h->state_ver & 0x7fffffff);
+  return S0;
+}
+}  // namespace
+
 // =================================================================================== C ABI
 #define API_BEGIN(h)              \
   if (!(h)) return 1;             \
@@ -1068,7 +1340,13 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
 
 int mps_destroy(mps_handle_t h) {
   if (!h) return 0;
+  if (h->grp) {
+    for (auto* s : h->grp->sub) mps_destroy(s);
+    delete h->grp;
+    h->grp = nullptr;
+  }
   cudaSetDevice(h->device);
+  for (auto& e : h->xev) if (e) cudaEventDestroy(e);
   cudaStreamSynchronize(h->stream);
   if (getenv("MPS_B200_DBG_MODE")) jacobi_print_phase_timing();
   for (auto& s : h->sites) if (s.d) cudaFreeAsync(s.d, h->stream);
@@ -1084,15 +1362,115 @@ int mps_destroy(mps_handle_t h) {
   return 0;
 }
 
+
+int mps_create_sharded(int n_qubits, int max_bond, double svd_cutoff, int gauge, int n_devices, const int* devices, int partition_by_cost,
+                       uint64_t seed, mps_handle_t* out) {
+  if (!out) return 1;
+  *out = nullptr;
+  if (n_devices < 1 || !devices) { g_create_error = "mps_create_sharded: empty device list"; return 2; }
+  mps_handle_t h = nullptr;
+  int rc = mps_create(n_qubits, 1, max_bond, svd_cutoff, gauge, devices[0], seed, &h);
+  if (rc) return rc;
+  if (n_devices == 1) { *out = h; return 0; }
+  try {
+    if (n_qubits < n_devices) throw std::runtime_error("mps_create_sharded: need at least one site per device");
+    ShardGroup* G = new ShardGroup;
+    h->grp = G;
+    G->bounds = shard_partition(n_qubits, n_devices, max_bond, partition_by_cost != 0);
+    G->owner.resize(n_qubits);
+    for (int d = 0; d < n_devices; ++d)
+      for (int k = G->bounds[d].first; k < G->bounds[d].second; ++k) G->owner[k] = d;
+    for (int d = 0; d < n_devices; ++d) {
+      mps_handle_t s = nullptr;
+      if (mps_create(n_qubits, 1, max_bond, svd_cutoff, gauge, devices[d], seed, &s)) throw std::runtime_error("device " + std::to_string(devices[d]) + ": " + g_create_error);
+      G->sub.push_back(s);
+    }
+    // direct NVLink paths between neighbouring devices: peer access for plain allocations and for the stream-ordered pool
+    for (int d = 0; d < n_devices; ++d)
+      for (int e : {d - 1, d + 1}) {
+        if (e < 0 || e >= n_devices || devices[e] == devices[d]) continue;   // a device may hold several blocks (single-GPU tests)
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, devices[d], devices[e]));
+        if (!can) continue;
+        CK(cudaSetDevice(devices[d]));
+        cudaError_t pe = cudaDeviceEnablePeerAccess(devices[e], 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
+        cudaGetLastError();
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, devices[e]));
+        cudaMemAccessDesc desc;
+        memset(&desc, 0, sizeof(desc));
+        desc.location.type = cudaMemLocationTypeDevice;
+        desc.location.id = devices[d];
+        desc.flags = cudaMemAccessFlagsProtReadWrite;
+        CK(cudaMemPoolSetAccess(pool, &desc, 1));
+      }
+    CK(cudaSetDevice(devices[0]));
+    *out = h;
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    mps_destroy(h);
+    return 2;
+  }
+}
+
+int mps_shard_layout(mps_handle_t h, int* n_devices, int* first_site /* n_devices + 1 entries, may be NULL */) {
+  API_BEGIN(h)
+  const int P = h->grp ? (int)h->grp->sub.size() : 1;
+  if (n_devices) *n_devices = P;
+  if (first_site) {
+    for (int d = 0; d < P; ++d) first_site[d] = h->grp ? h->grp->bounds[d].first : 0;
+    first_site[P] = h->ntot;
+  }
+  API_END(h)
+}
+
 const char* mps_last_error(mps_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int mps_reset(mps_handle_t h) { API_BEGIN(h) h->reset_state(); API_END(h) }
-int mps_snapshot(mps_handle_t h) { API_BEGIN(h) h->snapshot_state(); API_END(h) }
-int mps_restore(mps_handle_t h) { API_BEGIN(h) h->restore_state(); API_END(h) }
+int mps_reset(mps_handle_t h) {
+  API_BEGIN(h)
+  if (h->grp) {
+    h->queue.clear();
+    std::fill(h->has1q.begin(), h->has1q.end(), 0);
+    std::fill(h->last_touch.begin(), h->last_touch.end(), -1);
+    ++h->state_ver;
+    for (auto* s : h->grp->sub) { CK(cudaSetDevice(s->device)); s->reset_state(); }
+    CK(cudaSetDevice(h->device));
+  } else h->reset_state();
+  API_END(h)
+}
+int mps_snapshot(mps_handle_t h) {
+  API_BEGIN(h)
+  if (h->grp) {
+    h->flush();
+    for (auto* s : h->grp->sub) { CK(cudaSetDevice(s->device)); s->snapshot_state(); }
+    CK(cudaSetDevice(h->device));
+    h->has_snap = true;
+  } else h->snapshot_state();
+  API_END(h)
+}
+int mps_restore(mps_handle_t h) {
+  API_BEGIN(h)
+  if (h->grp) {
+    if (!h->has_snap) throw std::runtime_error("mps_restore without mps_snapshot");
+    h->flush();
+    ++h->state_ver;
+    for (auto* s : h->grp->sub) { CK(cudaSetDevice(s->device)); s->restore_state(); }
+    CK(cudaSetDevice(h->device));
+  } else h->restore_state();
+  API_END(h)
+}
 
 int mps_set_option(mps_handle_t h, const char* key, double value) {
   API_BEGIN(h)
   std::string k(key);
+  if (h->grp) {   // the coordinator keeps the queue-side options (fuse_1q, fuse_2q, layer_batch); the engines get everything
+    h->flush();
+    for (auto* s : h->grp->sub)
+      if (mps_set_option(s, key, value)) throw std::runtime_error(s->err);
+    CK(cudaSetDevice(h->device));
+  }
   // options that change how queued gates would be executed flush the queue first
   if (k == "cutoff_on_sqrt") { h->flush(); h->cutoff_on_sqrt = value != 0; }
   else if (k == "fuse_1q") { h->flush(); h->fuse_1q = value != 0; }
@@ -1140,95 +1518,112 @@ int mps_flush(mps_handle_t h) { API_BEGIN(h) h->flush(); API_END(h) }
 int mps_sync(mps_handle_t h) {
   API_BEGIN(h)
   h->flush();
+  if (h->grp)
+    for (auto* s : h->grp->sub) { CK(cudaSetDevice(s->device)); CK(cudaStreamSynchronize(s->stream)); }
+  CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   API_END(h)
 }
 
 int mps_norm(mps_handle_t h, int reg, double* out) {
   API_BEGIN(h)
-  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
-  h->flush();
-  if (h->norm_ver[reg] != h->state_ver) {
-    std::vector<std::array<double, 2>> w(h->nq, {1.0, 1.0});
-    h->norm_val[reg] = h->sweep_weights(reg, w).real();
-    h->norm_ver[reg] = h->state_ver;
+  mps_b200_handle* e = h->grp ? group_gather(h) : h;   // site-sharded group: evaluated by the engine of device 0
+  if (reg < 0 || reg >= e->nreg) throw std::runtime_error("bad register");
+  e->flush();
+  if (e->norm_ver[reg] != e->state_ver) {
+    std::vector<std::array<double, 2>> w(e->nq, {1.0, 1.0});
+    e->norm_val[reg] = e->sweep_weights(reg, w).real();
+    e->norm_ver[reg] = e->state_ver;
   }
-  *out = h->norm_val[reg];
+  *out = e->norm_val[reg];
   API_END(h)
 }
 int mps_expval_z(mps_handle_t h, int reg, int nq, const int* qubits, double* out) {
   API_BEGIN(h)
-  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
-  std::vector<std::array<double, 2>> w(h->nq, {1.0, 1.0});
+  mps_b200_handle* e = h->grp ? group_gather(h) : h;   // site-sharded group: evaluated by the engine of device 0
+  if (reg < 0 || reg >= e->nreg) throw std::runtime_error("bad register");
+  std::vector<std::array<double, 2>> w(e->nq, {1.0, 1.0});
   for (int i = 0; i < nq; ++i) {
-    if (qubits[i] < 0 || qubits[i] >= h->nq) throw std::runtime_error("qubit index out of range");
+    if (qubits[i] < 0 || qubits[i] >= e->nq) throw std::runtime_error("qubit index out of range");
     w[qubits[i]][1] = -w[qubits[i]][1];
   }
-  *out = h->sweep_weights(reg, w).real();
+  *out = e->sweep_weights(reg, w).real();
   API_END(h)
 }
 int mps_expval_z_all(mps_handle_t h, int reg, double* out_n) {
   API_BEGIN(h)
-  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
-  h->expval_z_all(reg, out_n);
+  mps_b200_handle* e = h->grp ? group_gather(h) : h;   // site-sharded group: evaluated by the engine of device 0
+  if (reg < 0 || reg >= e->nreg) throw std::runtime_error("bad register");
+  e->expval_z_all(reg, out_n);
   API_END(h)
 }
 int mps_expval_zz_pairs(mps_handle_t h, int reg, int npairs, const int* qi, const int* qj, double* out) {
   API_BEGIN(h)
-  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
-  h->expval_zz_pairs(reg, npairs, qi, qj, out);
+  mps_b200_handle* e = h->grp ? group_gather(h) : h;   // site-sharded group: evaluated by the engine of device 0
+  if (reg < 0 || reg >= e->nreg) throw std::runtime_error("bad register");
+  e->expval_zz_pairs(reg, npairs, qi, qj, out);
   API_END(h)
 }
 int mps_amplitude(mps_handle_t h, int reg, const int8_t* bits, double* out, size_t* len) {
   API_BEGIN(h)
-  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
+  mps_b200_handle* e = h->grp ? group_gather(h) : h;   // site-sharded group: evaluated by the engine of device 0
+  if (reg < 0 || reg >= e->nreg) throw std::runtime_error("bad register");
   std::vector<cplx> v;
-  h->amplitude(reg, bits, v);
+  e->amplitude(reg, bits, v);
   if (out) memcpy(out, v.data(), 16 * v.size());
   if (len) *len = v.size();
   API_END(h)
 }
 int mps_statevector(mps_handle_t h, int reg, double* out) {
   API_BEGIN(h)
-  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
-  if (h->nq > 30) throw std::runtime_error("state vector limited to 30 qubits");
-  std::vector<int8_t> bits(h->nq, -1);
+  mps_b200_handle* e = h->grp ? group_gather(h) : h;   // site-sharded group: evaluated by the engine of device 0
+  if (reg < 0 || reg >= e->nreg) throw std::runtime_error("bad register");
+  if (e->nq > 30) throw std::runtime_error("state vector limited to 30 qubits");
+  std::vector<int8_t> bits(e->nq, -1);
   std::vector<cplx> v;
-  h->amplitude(reg, bits.data(), v);
+  e->amplitude(reg, bits.data(), v);
   memcpy(out, v.data(), 16 * v.size());
   API_END(h)
 }
 
 int mps_measure(mps_handle_t h, int q) {
   API_BEGIN(h)
-  if (q < 0 || q >= h->nq) throw std::runtime_error("qubit index out of range");
-  h->measure.push_back(q);
+  mps_b200_handle* e = h->grp ? h->grp->sub[0] : h;
+  if (q < 0 || q >= e->nq) throw std::runtime_error("qubit index out of range");
+  e->measure.push_back(q);
   API_END(h)
 }
-int mps_clear_measure(mps_handle_t h) { API_BEGIN(h) h->measure.clear(); API_END(h) }
-int mps_seed(mps_handle_t h, uint64_t seed) { API_BEGIN(h) h->rng.seed(seed); API_END(h) }
+int mps_clear_measure(mps_handle_t h) { API_BEGIN(h) (h->grp ? h->grp->sub[0] : h)->measure.clear(); API_END(h) }
+int mps_seed(mps_handle_t h, uint64_t seed) { API_BEGIN(h) (h->grp ? h->grp->sub[0] : h)->rng.seed(seed); API_END(h) }
 
-int mps_sample(mps_handle_t h, int reg, int shots, char* out, int* n_out) {
+int mps_n_measured(mps_handle_t h, int* out) { API_BEGIN(h)
+  mps_b200_handle* e = h->grp ? h->grp->sub[0] : h; *out = (int)e->measure.size(); API_END(h) }
+
+int mps_sample(mps_handle_t h, int reg, int shots, char* out, size_t out_cap, int* n_out) {
   API_BEGIN(h)
-  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
-  const int nm = (int)h->measure.size();
+  mps_b200_handle* e = h->grp ? group_gather(h) : h;   // site-sharded group: evaluated by the engine of device 0
+  if (reg < 0 || reg >= e->nreg) throw std::runtime_error("bad register");
+  const int nm = (int)e->measure.size();
+  if (shots > 0 && (size_t)shots * (size_t)nm > out_cap)
+    throw std::runtime_error("mps_sample: output buffer too small (" + std::to_string(out_cap) + " chars for " + std::to_string(shots) + " shots x " +
+                             std::to_string(nm) + " measured qubits; see mps_n_measured)");
   int produced = 0;
   if (nm > 0 && shots > 0) {
-    if (h->nq < 20) {   // MAX_NUMBER_QUBITS_FOR_STATE_VEC, ExaTnMpsVisitor.cpp:55
+    if (e->nq < 20) {   // MAX_NUMBER_QUBITS_FOR_STATE_VEC, ExaTnMpsVisitor.cpp:55
       // GenerateSamples (GateMatrixAlgebra.hpp:125-156): draw, sort, walk the CDF in state-index order
-      std::vector<int8_t> bits(h->nq, -1);
+      std::vector<int8_t> bits(e->nq, -1);
       std::vector<cplx> sv;
-      h->amplitude(reg, bits.data(), sv);
+      e->amplitude(reg, bits.data(), sv);
       std::vector<double> rs;
       rs.reserve(shots + 1);
-      for (int i = 0; i < shots; ++i) rs.push_back(std::uniform_real_distribution<double>(0.0, 1.0)(h->rng));
+      for (int i = 0; i < shots; ++i) rs.push_back(std::uniform_real_distribution<double>(0.0, 1.0)(e->rng));
       std::sort(rs.begin(), rs.end());
       double csum = 0.0;
       size_t m = 0;
       for (size_t k = 0; k < sv.size(); ++k) {
         csum += std::norm(sv[k]);
         while (m < (size_t)shots && rs[m] < csum) {
-          for (int i = 0; i < nm; ++i) out[m * nm + i] = (k & (1ULL << h->measure[i])) ? '1' : '0';
+          for (int i = 0; i < nm; ++i) out[m * nm + i] = (k & (1ULL << e->measure[i])) ? '1' : '0';
           ++m;
         }
       }
@@ -1239,22 +1634,22 @@ int mps_sample(mps_handle_t h, int reg, int shots, char* out, int* n_out) {
         std::vector<int> res;
         std::vector<double> probs;
         for (int mi = 0; mi < nm; ++mi) {
-          const int q = h->measure[mi];
+          const int q = e->measure[mi];
           double pb[2];
           for (int b = 0; b < 2; ++b) {
-            std::vector<std::array<double, 2>> w(h->nq, {1.0, 1.0});
+            std::vector<std::array<double, 2>> w(e->nq, {1.0, 1.0});
             for (size_t j = 0; j < res.size(); ++j) {
-              const int qq = h->measure[j];
+              const int qq = e->measure[j];
               w[qq][res[j]] *= 1.0 / probs[j];
               w[qq][1 - res[j]] = 0.0;
             }
             w[q][1 - b] = 0.0;
-            pb[b] = h->sweep_weights(reg, w).real();
+            pb[b] = e->sweep_weights(reg, w).real();
           }
           const double PROB_EPS = 1e-12;
           const double p0 = std::fabs(pb[0]) < PROB_EPS ? 0.0 : pb[0];
           const double p1 = std::fabs(pb[1]) < PROB_EPS ? 0.0 : pb[1];
-          const double r = std::uniform_real_distribution<double>(0.0, 1.0)(h->rng);
+          const double r = std::uniform_real_distribution<double>(0.0, 1.0)(e->rng);
           const int bit = (r <= p0) ? 0 : 1;
           res.push_back(bit);
           probs.push_back(bit == 0 ? p0 : p1);
@@ -1271,14 +1666,14 @@ int mps_sample(mps_handle_t h, int reg, int shots, char* out, int* n_out) {
 int mps_bond_dims(mps_handle_t h, int* out) {
   API_BEGIN(h)
   h->flush();
-  for (int k = 0; k + 1 < h->ntot; ++k) out[k] = h->sites[k].dr;
+  for (int k = 0; k + 1 < h->ntot; ++k) out[k] = (h->grp ? h->grp->sub[h->grp->owner[k]] : h)->sites[k].dr;
   API_END(h)
 }
 int mps_singular_values(mps_handle_t h, int bond, double* out, int cap, int* count) {
   API_BEGIN(h)
   h->flush();
   if (bond < 0 || bond >= h->ntot - 1) throw std::runtime_error("bad bond index");
-  const auto& v = h->sv[bond];
+  const auto& v = (h->grp ? h->grp->sub[h->grp->owner[bond]] : h)->sv[bond];   // a bond's gates run on the owner of its left site
   const int c = std::min<int>(cap, (int)v.size());
   for (int i = 0; i < c; ++i) out[i] = v[i];
   if (count) *count = (int)v.size();
@@ -1288,17 +1683,34 @@ int mps_discarded_weight(mps_handle_t h, double* out) {
   API_BEGIN(h)
   h->flush();
   *out = h->discarded;
+  if (h->grp) for (auto* s : h->grp->sub) *out += s->discarded;
   API_END(h)
+}
+int mps_fidelity_estimate(mps_handle_t h, double* out) {
+  API_BEGIN(h)
+  h->flush();
+  double lf = h->log_fidelity;
+  if (h->grp) for (auto* s : h->grp->sub) lf += s->log_fidelity;
+  *out = std::exp(lf);
+  API_END(h)
+}
+// a site of a group lives in the engine of its owner device
+static mps_b200_handle* site_engine(mps_handle_t h, int k) {
+  if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
+  if (!h->grp) return h;
+  mps_b200_handle* e = h->grp->sub[h->grp->owner[k]];
+  CK(cudaSetDevice(e->device));
+  return e;
 }
 int mps_get_site(mps_handle_t h, int k, double* out, int shape[3]) {
   API_BEGIN(h)
   h->flush();
-  if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
-  const SiteBuf& s = h->sites[k];
+  mps_b200_handle* e = site_engine(h, k);
+  const SiteBuf& s = e->sites[k];
   shape[0] = s.dl; shape[1] = 2; shape[2] = s.dr;
   if (out) {
-    CK(cudaMemcpyAsync(out, s.d, (size_t)2 * s.dl * s.dr * 16, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(out, s.d, (size_t)2 * s.dl * s.dr * 16, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
   }
   API_END(h)
 }
@@ -1306,19 +1718,21 @@ int mps_set_site(mps_handle_t h, int k, const double* in, int dl, int dr) {
   API_BEGIN(h)
   h->flush();
   ++h->state_ver;   // the caller may change the tensor
-  if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
-  h->ensure_site(k, dl, dr, false);
-  CK(cudaMemcpyAsync(h->sites[k].d, in, (size_t)2 * dl * dr * 16, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  mps_b200_handle* e = site_engine(h, k);
+  ++e->state_ver;
+  e->ensure_site(k, dl, dr, false);
+  CK(cudaMemcpyAsync(e->sites[k].d, in, (size_t)2 * dl * dr * 16, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
   API_END(h)
 }
 int mps_site_device_ptr(mps_handle_t h, int k, void** dptr, int shape[3]) {
   API_BEGIN(h)
   h->flush();
   ++h->state_ver;   // the caller may change the tensor
-  CK(cudaStreamSynchronize(h->stream));
-  if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
-  const SiteBuf& s = h->sites[k];
+  mps_b200_handle* e = site_engine(h, k);
+  ++e->state_ver;
+  CK(cudaStreamSynchronize(e->stream));
+  const SiteBuf& s = e->sites[k];
   *dptr = s.d;
   shape[0] = s.dl; shape[1] = 2; shape[2] = s.dr;
   API_END(h)
@@ -1327,19 +1741,32 @@ int mps_resize_site(mps_handle_t h, int k, int dl, int dr, void** dptr) {
   API_BEGIN(h)
   h->flush();
   ++h->state_ver;   // the caller may change the tensor
-  if (k < 0 || k >= h->ntot) throw std::runtime_error("bad site index");
-  h->ensure_site(k, dl, dr, false);
-  CK(cudaStreamSynchronize(h->stream));
-  *dptr = h->sites[k].d;
+  mps_b200_handle* e = site_engine(h, k);
+  ++e->state_ver;
+  e->ensure_site(k, dl, dr, false);
+  CK(cudaStreamSynchronize(e->stream));
+  *dptr = e->sites[k].d;
   API_END(h)
 }
 int mps_stats(mps_handle_t h, double* out, int cap) {
   API_BEGIN(h)
   h->flush();
   CK(cudaStreamSynchronize(h->stream));
-  const double v[13] = {h->n2q, h->n1q, h->nlayers, h->nsweeps, h->nlaunch, h->ms_theta, h->ms_svd, h->ms_wb, h->ms_qr, jacobi_dmma_flops(), h->nfused2q,
-                        h->nonconverged, h->guard_violations};
-  for (int i = 0; i < cap && i < 13; ++i) out[i] = v[i];
+  double v[15] = {h->n2q, h->n1q, h->nlayers, h->nsweeps, h->nlaunch, h->ms_theta, h->ms_svd, h->ms_wb, h->ms_qr, 0.0, h->nfused2q,
+                  h->nonconverged, h->guard_violations, 0.0, 0.0};
+  if (h->grp) {
+    for (auto* s : h->grp->sub) {
+      CK(cudaSetDevice(s->device));
+      CK(cudaStreamSynchronize(s->stream));
+      const double w[13] = {s->n2q, s->n1q, s->nlayers, s->nsweeps, s->nlaunch, s->ms_theta, s->ms_svd, s->ms_wb, s->ms_qr, jacobi_dmma_flops(), 0.0,
+                            s->nonconverged, s->guard_violations};
+      for (int i = 0; i < 13; ++i) v[i] += w[i];
+    }
+    v[13] = h->grp->exchanges;
+    v[14] = h->grp->bytes_moved;
+    CK(cudaSetDevice(h->device));
+  } else v[9] = jacobi_dmma_flops();
+  for (int i = 0; i < cap && i < 15; ++i) out[i] = v[i];
   API_END(h)
 }
 

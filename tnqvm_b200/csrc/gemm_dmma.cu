@@ -326,7 +326,12 @@ int gemm_tiles(int M, int N, int mode) {
 }
 
 static void set_attrs() {
-  static bool attr_set = false;
+  // function attributes belong to a device context: once per device (site-sharded handles drive several from one process,
+  // one host thread each; setting the same value twice from two threads is harmless)
+  static bool attr_set_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& attr_set = attr_set_dev[dev & 63];
   if (attr_set) return;
   cudaFuncSetAttribute(zgemm_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   cudaFuncSetAttribute(zgemm_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);

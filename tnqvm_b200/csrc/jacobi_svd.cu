@@ -517,6 +517,15 @@ __global__ void __launch_bounds__(256) trunc_kernel(const TruncProblem* __restri
   __syncthreads();
   __shared__ int s_keep;
   __shared__ double s_rn;
+  // numerically-null singular values stand for exact zeros (engine.cu, null_tol): report them as 0.0 so that the reference's cut
+  // rule below sees what an exact SVD would have returned
+  {
+    const double s0 = P.sigma[0];
+    __syncthreads();
+    for (int k = tid; k < N; k += 256)
+      if (k > 0 && P.sigma[k] <= null_tol * s0) P.sigma[k] = 0.0;
+    __syncthreads();
+  }
   if (tid == 0) {
     // truncateSvdTensors, ExaTnMpsVisitor.cpp:2434-2445: first k whose partial norm is below eps, PLUS ONE
     int cut = N;

@@ -373,7 +373,10 @@ void launch_qr(const QrProblem* d_probs, int batch, int max_m, int max_n, cudaSt
   // the panel is staged in shared memory whenever it fits (the kernel applies the same test per matrix)
   const size_t want = (size_t)max_m * PB * sizeof(double2);
   const int smem = (int)(want < (size_t)PANEL_SMEM_CAP ? want : (size_t)PANEL_SMEM_CAP);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // per device context (several devices in one process: site-sharded handles)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& attr_set = attr_set_dev[dev & 63];
   if (!attr_set) {
     cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_CAP);
     attr_set = true;

@@ -139,10 +139,11 @@ void B200MpsVisitor::finalize() {
       check(mps_expval_z(m_handle, 0, (int)q.size(), q.data(), &ez), "expval_z");
       m_buffer->addExtraInfo("exp-val-z", ez);
     } else if (m_shotCount >= 1) {
-      const int nm = (int)m_measureQubits.size();
+      int nm = 0;   // the handle's own measure list sets the stride of a sample string
+      check(mps_n_measured(m_handle, &nm), "n_measured");
       std::vector<char> out((size_t)m_shotCount * nm + 1);
       int produced = 0;
-      check(mps_sample(m_handle, 0, m_shotCount, out.data(), &produced), "sample");
+      check(mps_sample(m_handle, 0, m_shotCount, out.data(), out.size(), &produced), "sample");
       for (int s = 0; s < produced; ++s) m_buffer->appendMeasurement(std::string(out.data() + (size_t)s * nm, nm));
     }
   }

@@ -7,6 +7,7 @@
 // The nearest-neighbour pass restates the meet-in-the-middle Swap ladder of "lnn-transform"
 // (tnqvm/visitors/exatn-mps/NearestNeighborTransform.hpp:43-135); the accelerator itself calls XACC's external "nnizer".
 #include <cctype>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -179,6 +180,8 @@ int main(int argc, char** argv) {
   int nq = 0, shots = -1, maxBond = 0, seed = -1, device = 0, gauge = 0;
   double cutoff = -1.0;
   bool wantState = false, dumpNN = false, fuse2q = false;
+  int repeat = 1;   // run execute() this many times on the same visitor instance (TNQVM.cpp:109 reuses it); every wall time is reported
+  std::vector<double> executeMs;
   std::string bitstring, observe;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
@@ -195,6 +198,7 @@ int main(int argc, char** argv) {
     else if (a == "--dump-nn") dumpNN = true;   // print the nearest-neighbourised program and exit (no GPU needed)
     else if (a == "--bitstring") bitstring = next();
     else if (a == "--fuse-2q") fuse2q = true;
+    else if (a == "--repeat") repeat = std::max(1, atoi(next().c_str()));
     else if (a == "--observe") observe = next();   // VQE mode: semicolon-separated Pauli words, e.g. "X0X1;Y0Y1;Z0;Z1"
     else { fprintf(stderr, "usage: b200_tnqvm_run --xasm FILE|- [--qubits N] [--shots S] [--max-bond-dim D] [--svd-cutoff E] [--seed K] [--state] [--bitstring 01x1..] [--fuse-2q] [--observe \"X0X1;Z0\"]\n"); return 2; }
   }
@@ -238,8 +242,14 @@ int main(int argc, char** argv) {
       std::stringstream ts(observe);
       for (std::string t; std::getline(ts, t, ';');) if (!t.empty()) terms.push_back(t);
       vqeTerms = executeVqe(visitor, opts, buffer, kernel, terms, shots);
-    } else
-      execute(visitor, opts, buffer, kernel, shots);
+    } else {
+      for (int r = 0; r < repeat; ++r) {
+        if (r) buffer = std::make_shared<AcceleratorBuffer>("q", nq);
+        const auto t0 = std::chrono::steady_clock::now();
+        execute(visitor, opts, buffer, kernel, shots);
+        executeMs.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+      }
+    }
     printf("{\"visitor\": \"%s\", \"qubits\": %d, \"instructions\": %d, \"instructions_after_nn\": %d", visitor->name().c_str(), nq, nInst,
            kernel->nInstructions());
     for (auto& kv : buffer->getInformation())
@@ -258,6 +268,11 @@ int main(int argc, char** argv) {
       const auto& im = std::get<std::vector<double>>((*buffer)["amplitude-imag-vec"]);
       printf(", \"amplitude_slice\": [");
       for (size_t i = 0; i < re.size(); ++i) printf("%s[%.17g, %.17g]", i ? ", " : "", re[i], im[i]);
+      printf("]");
+    }
+    if (!executeMs.empty()) {
+      printf(", \"execute_ms\": [");
+      for (size_t i = 0; i < executeMs.size(); ++i) printf("%s%.3f", i ? ", " : "", executeMs[i]);
       printf("]");
     }
     if (!observe.empty()) {

@@ -42,13 +42,24 @@ class CompiledCircuit:
 
 class B200MPS:
     def __init__(self, n_qubits, max_bond=0, svd_cutoff=-1.0, gauge=GAUGE_REFERENCE, device=0, seed=0, n_registers=1,
-                 **options):
+                 devices=None, partition_by="cost", **options):
+        """devices = [d0, d1, ...]: the sites are sharded over these GPUs inside the library (mps_create_sharded: contiguous
+        site blocks, boundary sites exchanged by peer copies over NVLink); otherwise one engine on `device`."""
         self.L = abi.load_library()
         self.n = n_qubits
         self.nreg = n_registers
         self.h = C.c_void_p()
-        rc = self.L.mps_create(n_qubits, n_registers, int(max_bond), float(svd_cutoff), int(gauge), int(device), int(seed),
-                               C.byref(self.h))
+        if devices is not None and len(devices) > 1:
+            if n_registers != 1:
+                raise ValueError("a site-sharded handle holds one register")
+            dv = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.L.mps_create_sharded(n_qubits, int(max_bond), float(svd_cutoff), int(gauge), len(devices), dv,
+                                           int(partition_by == "cost"), int(seed), C.byref(self.h))
+        else:
+            if devices:
+                device = devices[0]
+            rc = self.L.mps_create(n_qubits, n_registers, int(max_bond), float(svd_cutoff), int(gauge), int(device), int(seed),
+                                   C.byref(self.h))
         if rc != 0:
             msg = self.L.mps_last_error(None)
             self.h = None
@@ -183,12 +194,18 @@ class B200MPS:
     def seed(self, s):
         self._ck(self.L.mps_seed(self.h, int(s)))
 
+    def n_measured(self):
+        out = C.c_int()
+        self._ck(self.L.mps_n_measured(self.h, C.byref(out)))
+        return out.value
+
     def sample(self, shots, reg=0):
-        nq = max(1, self.n)
-        buf = C.create_string_buffer(shots * nq + 1)
+        """(raw chars, strings produced); the stride of a string is n_measured() (the handle's own measure list, which
+        grows with every Measure until reset() / clear_measure())."""
+        cap = max(1, shots) * max(1, self.n_measured())
+        buf = C.create_string_buffer(cap + 1)
         n_out = C.c_int()
-        self._ck(self.L.mps_sample(self.h, reg, shots, buf, C.byref(n_out)))
-        # the number of measured qubits is known to the handle; recover the stride from the caller
+        self._ck(self.L.mps_sample(self.h, reg, shots, buf, cap, C.byref(n_out)))
         return buf.raw, n_out.value
 
     def sample_strings(self, shots, n_measured, reg=0):
@@ -211,6 +228,12 @@ class B200MPS:
     def discarded_weight(self):
         out = C.c_double()
         self._ck(self.L.mps_discarded_weight(self.h, C.byref(out)))
+        return out.value
+
+    def fidelity_estimate(self):
+        """prod over truncations of (1 - discarded/total weight)"""
+        out = C.c_double()
+        self._ck(self.L.mps_fidelity_estimate(self.h, C.byref(out)))
         return out.value
 
     def get_site(self, k):
@@ -242,9 +265,18 @@ class B200MPS:
         self._ck(self.L.mps_get_stream(self.h, C.byref(p)))
         return p.value or 0
 
+    def shard_layout(self):
+        """First site of every device block (+ n at the end); [0, n] for a single-device handle."""
+        nd = C.c_int()
+        self._ck(self.L.mps_shard_layout(self.h, C.byref(nd), None))
+        first = (C.c_int * (nd.value + 1))()
+        self._ck(self.L.mps_shard_layout(self.h, C.byref(nd), first))
+        return list(first)
+
     def stats(self):
-        out = np.zeros(13, dtype=np.float64)
-        self._ck(self.L.mps_stats(self.h, out.ctypes.data, 13))
+        out = np.zeros(15, dtype=np.float64)
+        self._ck(self.L.mps_stats(self.h, out.ctypes.data, 15))
         keys = ["gates_2q", "gates_1q_kernel", "layers", "jacobi_sweeps", "launches", "ms_theta", "ms_svd", "ms_writeback", "ms_qr",
-                "jacobi_dmma_flops", "gates_2q_fused", "svd_nonconverged", "norm_guard_violations"]
+                "jacobi_dmma_flops", "gates_2q_fused", "svd_nonconverged", "norm_guard_violations", "boundary_exchanges",
+                "peer_bytes"]
         return dict(zip(keys, out.tolist()))
