@@ -104,11 +104,11 @@ def test_golden_fixtures_on_gpu():
         e.close()
 
 
-@pytest.mark.parametrize("opts", [dict(qr_prereduce=0), dict(jacobi_wide_tasks=0, jacobi_ctas_per_sm=4),
+@pytest.mark.parametrize("opts", [dict(qr_prereduce=0), dict(jacobi_cluster=1), dict(jacobi_cluster=1, qr_prereduce=0, jacobi_chunk_mb=1), dict(jacobi_wide_tasks=0, jacobi_ctas_per_sm=4),
                                   dict(jacobi_wide_tasks=1, jacobi_ctas_per_sm=2), dict(jacobi_wide_tasks=0, jacobi_ctas_per_sm=1),
                                   dict(jacobi_chunk_mb=1, l2_persist=0), dict(jacobi_chunk_mb=1, l2_persist=1)],
-                         ids=["no_qr", "narrow_tasks_4_per_sm", "wide_tasks_2_per_sm", "narrow_tasks_1_per_sm", "chunked_no_window",
-                              "chunked_l2_window"])
+                         ids=["no_qr", "cluster_resident_tasks", "cluster_resident_tasks_no_qr_chunked", "narrow_tasks_4_per_sm", "wide_tasks_2_per_sm", "narrow_tasks_1_per_sm",
+                              "chunked_no_window", "chunked_l2_window"])
 def test_svd_engine_variants_agree_with_oracle(O, opts):
     """Every SVD configuration (QR pre-reduction on/off, resident CTAs / warps per pair task, one chunk per layer vs many
     chunks, persisting-L2 window on/off) must give the reference's observables: exact run at 1e-10, truncated at TRUNC_TOL."""

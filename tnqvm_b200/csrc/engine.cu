@@ -11,6 +11,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <cfloat>
@@ -180,6 +181,13 @@ struct mps_b200_handle {
   // L2-resident over its sweeps (126 MB L2) instead of streaming from HBM at every tournament step.  chi=256 layers
   // (25 x 4 MiB) are one chunk, a chi=1024 theta (64 MiB) is a chunk of its own.
   int chunk_mb = 96;
+  // 0 (default): the streaming sweep kernel (jacobi_svd.cu).  1: pair tasks resident in shared memory, split by rows over
+  // thread-block clusters (jacobi_cluster.cu) -- parity-tested, but measured 2.5x SLOWER on the saturated chi=256 step
+  // (144 vs 58 ms, profiles/r04h_*): a resident 16-column pair costs 128 KB of shared memory, so only 148 tasks are in flight
+  // against 592 for the streaming kernel, and the per-task latency chain (dependency wait, bulk load, Gram, two cluster
+  // barriers around the leader's rotation phase, update) is ~24 us.  Kept as an experiment, see DESIGN.md section 4.
+  int jacobi_cluster = 0;
+  std::map<std::pair<int, int>, int> cluster_cap;   // (cluster size, rows per CTA) -> co-resident clusters on this device
   int l2_persist = 1;      // access-policy window (persisting L2 lines) over the Jacobi matrices of the running chunk
   size_t l2_persist_max = 0, l2_window_max = 0;
   double guard_violations = 0;   // norm-guard failures seen with norm_guard = 2
@@ -462,8 +470,9 @@ struct mps_b200_handle {
     const size_t oGat = ws.reserve(sizeof(GatherProblem) * B);
     const size_t oGemm2 = ws.reserve(sizeof(GemmProblem) * B);
     const size_t oQr = ws.reserve(sizeof(QrProblem) * B);
-    int pstride = 2;   // progress flags per matrix of the persistent sweep kernel: one per 8-column block
+    int pstride = 2;   // progress flags per matrix of the persistent sweep kernels: one per 8-column block (x one per cluster rank)
     for (int b = 0; b < B; ++b) pstride = std::max(pstride, ((D[b].Ng + 7) / 8 + 1) & ~1);
+    pstride *= jacobi_cluster_progress_ints_per_block();
     const size_t oProg = ws.reserve(sizeof(int) * ((size_t)B * pstride + (size_t)(max_sweeps + 4) * (B + 1)));   // progress flags, then one task counter per (chunk, sweep)
     const size_t oActive = ws.reserve(sizeof(int) * 2 * (B + 2));   // per chunk: [0] matrices still rotating, [1..] their indices (within the chunk)
     const size_t oFlags = ws.reserve(sizeof(int) * (4 * B + 4) + sizeof(double) * B + 16);   // dirty[B], done[B], per chunk (remaining, fault), pad, fro2[B]
@@ -507,12 +516,12 @@ struct mps_b200_handle {
     char* wb = ws.base;
 
     // Jacobi chunks: consecutive matrices whose work matrices fit `chunk_mb` together
-    struct Chunk { int c0, c1, pairs, steps; long tasks; size_t bytes; };
+    struct Chunk { int c0, c1, pairs, steps; long tasks; size_t bytes; int maxM; };
     std::vector<Chunk> chunks;
     {
       const size_t budget = (size_t)std::max(1, chunk_mb) << 20;
       for (int c0 = 0; c0 < B;) {
-        Chunk c{c0, c0, 1, 1, 0, 0};
+        Chunk c{c0, c0, 1, 1, 0, 0, 1};
         while (c.c1 < B) {
           const Dim& d = D[c.c1];
           const size_t sz = sizeof(double2) * (size_t)d.Mj * d.Ng;
@@ -521,6 +530,7 @@ struct mps_b200_handle {
           const int nb = (d.Ng + 7) / 8, nbe = (nb == 1) ? 1 : ((nb + 1) & ~1);
           const int np = nb == 1 ? 1 : nbe / 2;
           c.pairs = std::max(c.pairs, np);
+          c.maxM = std::max(c.maxM, d.Mj);
           c.steps = std::max(c.steps, nb == 1 ? 1 : nbe - 1);
           c.tasks += np;
           ++c.c1;
@@ -650,9 +660,29 @@ struct mps_b200_handle {
           av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
           CK(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
         }
+        int ccs = 0, crpc = 0, cmaxc = 0;
+        bool use_cluster = jacobi_cluster && jacobi_cluster_shape(ck.maxM, &ccs, &crpc);
+        if (use_cluster) {
+          auto key = std::make_pair(ccs, crpc);
+          auto it = cluster_cap.find(key);
+          if (it == cluster_cap.end()) it = cluster_cap.emplace(key, jacobi_cluster_max_clusters(ccs, crpc)).first;
+          cmaxc = it->second;
+          if (cmaxc < 1) use_cluster = false;
+        }
         int rotating = CB, csweep = 0, queued = 0, seen = 0;
         volatile int* h_crem = (volatile int*)(h_rem + 2 * (size_t)(max_sweeps + 4) * nchunk);
         auto enqueue = [&]() {
+          if (use_cluster) {
+            if (launch_jacobi_cluster_sweep(dJ + c0, rotating, cpairs, csteps, queued * csteps, tol2, dead2, d_fro2 + c0, d_dirty + c0, d_done + c0,
+                                            d_prog + (size_t)c0 * pstride, pstride, d_crem + 1, d_active, ccs, crpc, cmaxc, stream) < 0)
+              throw std::runtime_error(std::string("cluster Jacobi launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+            launch_jacobi_check(CB, d_dirty + c0, d_done + c0, d_crem, d_active, stream);
+            nlaunch += 2;
+            CK(cudaMemcpyAsync((void*)(h_crem + 2 * queued), d_crem, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaEventRecord(sev[queued & 1], stream));
+            ++queued;
+            return;
+          }
           int per_sm = ctas_per_sm, warps = 4;
           // live tasks per tournament step (finished matrices have no slots: d_active); phantom slots of the smaller
           // matrices of the chunk still cost one dequeue each, so a CTA should not walk through more than ~100 per sweep
@@ -1317,13 +1347,14 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     // developer overrides for A/B runs of the whole test-suite
     if (const char* e = getenv("MPS_B200_QR")) h->use_qr = atoi(e) != 0;
     if (const char* e = getenv("MPS_B200_MAX_SWEEPS")) h->max_sweeps = std::max(1, std::min(1000, atoi(e)));
-    if (const char* e = getenv("MPS_B200_DBG_MODE")) jacobi_set_debug_mode(atoi(e));
+    if (const char* e = getenv("MPS_B200_DBG_MODE")) { jacobi_set_debug_mode(atoi(e)); jacobi_cluster_set_debug(atoi(e)); }
     h->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("MPS_B200_JACOBI_TOL")) h->jacobi_tol = atof(e);
     if (const char* e = getenv("MPS_B200_NULL_TOL")) h->null_tol = atof(e);
     if (const char* e = getenv("MPS_B200_WIDE_TASKS")) h->wide_tasks = atoi(e) != 0;
     if (const char* e = getenv("MPS_B200_CHUNK_MB")) h->chunk_mb = std::max(1, atoi(e));
     if (const char* e = getenv("MPS_B200_L2_PERSIST")) h->l2_persist = atoi(e) != 0;
+    if (const char* e = getenv("MPS_B200_JACOBI_CLUSTER")) h->jacobi_cluster = atoi(e) != 0;
     if (const char* e = getenv("MPS_B200_CTAS_PER_SM")) h->ctas_per_sm = std::max(0, std::min(4, atoi(e)));
     if (const char* e = getenv("MPS_B200_SMALL_GEMM")) gemm_set_small_path(atoi(e));
     if (seed) h->rng.seed(seed);
@@ -1348,7 +1379,7 @@ int mps_destroy(mps_handle_t h) {
   cudaSetDevice(h->device);
   for (auto& e : h->xev) if (e) cudaEventDestroy(e);
   cudaStreamSynchronize(h->stream);
-  if (getenv("MPS_B200_DBG_MODE")) jacobi_print_phase_timing();
+  if (getenv("MPS_B200_DBG_MODE")) { jacobi_print_phase_timing(); jacobi_cluster_print_phase_timing(); }
   for (auto& s : h->sites) if (s.d) cudaFreeAsync(s.d, h->stream);
   for (auto& s : h->snap) if (s.d) cudaFreeAsync(s.d, h->stream);
   cudaStreamSynchronize(h->stream);
@@ -1486,6 +1517,7 @@ int mps_set_option(mps_handle_t h, const char* key, double value) {
   else if (k == "jacobi_ctas_per_sm") { h->flush(); h->ctas_per_sm = std::max(0, std::min(4, (int)value)); }
   else if (k == "jacobi_chunk_mb") { h->flush(); h->chunk_mb = std::max(1, (int)value); }
   else if (k == "l2_persist") { h->flush(); h->l2_persist = value != 0; }
+  else if (k == "jacobi_cluster") { h->flush(); h->jacobi_cluster = value != 0; }
   else if (k == "norm_guard") { h->flush(); h->norm_guard = std::max(0, std::min(2, (int)value)); }
   else if (k == "max_bond") { h->flush(); h->max_bond = value > 0 ? (int)value : INT_MAX - 1; }
   else if (k == "svd_cutoff") { h->flush(); h->cutoff = value >= 0 ? value : DBL_MIN; }
@@ -1758,14 +1790,14 @@ int mps_stats(mps_handle_t h, double* out, int cap) {
     for (auto* s : h->grp->sub) {
       CK(cudaSetDevice(s->device));
       CK(cudaStreamSynchronize(s->stream));
-      const double w[13] = {s->n2q, s->n1q, s->nlayers, s->nsweeps, s->nlaunch, s->ms_theta, s->ms_svd, s->ms_wb, s->ms_qr, jacobi_dmma_flops(), 0.0,
+      const double w[13] = {s->n2q, s->n1q, s->nlayers, s->nsweeps, s->nlaunch, s->ms_theta, s->ms_svd, s->ms_wb, s->ms_qr, jacobi_dmma_flops() + jacobi_cluster_dmma_flops(), 0.0,
                             s->nonconverged, s->guard_violations};
       for (int i = 0; i < 13; ++i) v[i] += w[i];
     }
     v[13] = h->grp->exchanges;
     v[14] = h->grp->bytes_moved;
     CK(cudaSetDevice(h->device));
-  } else v[9] = jacobi_dmma_flops();
+  } else v[9] = jacobi_dmma_flops() + jacobi_cluster_dmma_flops();
   for (int i = 0; i < cap && i < 15; ++i) out[i] = v[i];
   API_END(h)
 }

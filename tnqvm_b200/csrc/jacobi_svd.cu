@@ -316,6 +316,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     double2* const baseB = (blkB >= 0) ? G + (size_t)ldg * (blkB * 8) : G;
     const int nA = min(8, N - blkA * 8), nB = (blkB >= 0) ? min(8, N - blkB * 8) : 0;
     for (int row = tid; row < M; row += NT) {
+      asm volatile("" ::: "memory");   // keeps the loop-invariant loads of s_tp / s_tq at their point of use (else: hoisted into local memory)
       double2 x[16];
       {
         const double2* pa = baseA + row;

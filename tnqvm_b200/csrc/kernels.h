@@ -68,6 +68,17 @@ void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs,
                          const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_counter,
                          int* d_fault /* += 1 if a dependency wait timed out */, int grid_ctas, int warps_per_task /* 4 or 8 */,
                          const int* d_active, cudaStream_t s);
+// The same sweep with shared-memory-resident pair tasks split by rows over thread-block clusters (jacobi_cluster.cu).  Progress flags:
+// jacobi_cluster_progress_ints_per_block() ints per 8-column block (one per cluster rank); no task counter (static assignment).
+int jacobi_cluster_progress_ints_per_block();
+bool jacobi_cluster_shape(int max_m, int* cs, int* rpc_cap);          // cluster size / rows per CTA for matrices of up to max_m rows
+int jacobi_cluster_max_clusters(int cs, int rpc_cap);                 // co-resident clusters on the current device
+int launch_jacobi_cluster_sweep(const JacobiProblem* d_probs, int batch, int max_pairs, int nsteps, int base, double tol2, double dead2,
+                                const double* d_fro2, int* d_dirty, const int* d_done, int* d_progress, int progress_stride, int* d_fault,
+                                const int* d_active, int cs, int rpc_cap, int max_clusters, cudaStream_t s);   // CTAs launched, -1 on error
+double jacobi_cluster_dmma_flops();
+void jacobi_cluster_set_debug(int mode);   // timing experiments only
+void jacobi_cluster_print_phase_timing();
 void jacobi_set_debug_mode(int mode);   // timing experiments only
 void jacobi_print_phase_timing();
 double jacobi_dmma_flops();   // process-wide count of the FP64 flops the Jacobi pair tasks executed (Gram on DMMA + scaled rotations)
