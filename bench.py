@@ -230,6 +230,7 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")   # host-side barrier: an NCCL barrier would park a spinning kernel on the idle GPUs
 
     def barrier():
         if dist is not None:
@@ -403,6 +404,52 @@ def run_b200(args):
         except Exception as ex:   # reported, never silently dropped
             e2e_visitor = {"error": repr(ex)[:300]}
 
+    # ---- strong scaling of ONE circuit: sites sharded over the N GPUs of the box inside the library (mps_create_sharded, SURVEY 8e /
+    # configs 3 and 5).  The launch contract gives one process per GPU; a site-sharded handle is one process driving N devices,
+    # so rank 0 runs it over all N GPUs while the other ranks wait at a barrier with their GPUs idle.
+    sharded = None
+    if world > 1 and not args.no_extras:
+        barrier()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            sharded = {"n_devices": world, "timing": "host wall clock around run + sync, best of 2 after one untimed pass", "circuits": []}
+            for label, nq_s, depth_s, chi_s in (("c2_brickwork_n%d_depth%d_chi%d" % (n, args.depth, chi), n, args.depth, chi),
+                                                ("brickwork_n%d_depth%d_chi512" % (n, args.depth), n, args.depth, 512)):
+                circ_s = Cc.brickwork(nq_s, depth_s, seed=seed)
+                cc_s = tnqvm_b200.CompiledCircuit(circ_s)
+                res = {}
+                for tag, devs in (("1gpu", [local]), ("sharded", list(range(world)))):
+                    es = tnqvm_b200.B200MPS(nq_s, max_bond=chi_s, devices=devs)
+                    best = 1e30
+                    for r in range(3):
+                        es.reset(); es.sync()
+                        t0 = time.perf_counter()
+                        es.run(cc_s); es.sync()
+                        if r:
+                            best = min(best, time.perf_counter() - t0)
+                    st_s = es.stats()
+                    res[tag] = dict(ms=best * 1e3, z=es.expval_z_all(), norm=es.norm(), layout=es.shard_layout(), exch=st_s["boundary_exchanges"] / 3,
+                                    mb=st_s["peer_bytes"] / 3e6)
+                    # the metric's own unit of work on this handle: saturated-state steps (two brickwork layers each) after the circuit
+                    sat_steps = [tnqvm_b200.CompiledCircuit(step_circuit(nq_s, 100 + i, seed)) for i in range(4)]
+                    es.run(sat_steps[0]); es.sync()
+                    t0 = time.perf_counter()
+                    for i in range(1, 4):
+                        es.run(sat_steps[i]); es.flush()
+                    es.sync()
+                    res[tag]["step_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+                    es.close()
+                sharded["circuits"].append({
+                    "name": label, "gates_2q": Cc.count_gates(circ_s)[1], "wall_ms_1gpu": res["1gpu"]["ms"], "wall_ms_sharded": res["sharded"]["ms"],
+                    "speedup_vs_1gpu": res["1gpu"]["ms"] / res["sharded"]["ms"], "site_blocks": res["sharded"]["layout"],
+                    "saturated_step_ms_1gpu": res["1gpu"]["step_ms"], "saturated_step_ms_sharded": res["sharded"]["step_ms"],
+                    "saturated_step_gates_per_s_sharded": (nq_s - 1) / (res["sharded"]["step_ms"] * 1e-3),
+                    "saturated_step_speedup_vs_1gpu": res["1gpu"]["step_ms"] / res["sharded"]["step_ms"],
+                    "boundary_exchanges": res["sharded"]["exch"], "peer_mbytes": res["sharded"]["mb"],
+                    "parity_max_abs_dz_vs_1gpu": float(np.abs(res["1gpu"]["z"] - res["sharded"]["z"]).max()),
+                    "parity_rel_dnorm_vs_1gpu": abs(res["1gpu"]["norm"] - res["sharded"]["norm"]) / abs(res["1gpu"]["norm"])})
+        dist.barrier(group=cpu_group)
+
     # ---- CPU baseline beside it (rank 0, N = 1): the oracle on a bounded sample of the same step, same state
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -456,6 +503,7 @@ def run_b200(args):
                         "gates_2q_per_s": n2_0 / (circuit_ms * 1e-3), "launches": int(st1["launches"] - st0["launches"])},
             "roofline_theta_chi512": theta512,
             "e2e_visitor": e2e_visitor,
+            "circuit_sharded": sharded,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -5,9 +5,10 @@ outputs, and the size-independent checks that exist at this size.  One JSON line
       gate (reference-faithful) and with option fuse_2q (CX.Rz.CX -> one ZZ gate).  Routing the wrap edge drags a qubit
       through the whole chain, the bonds reach 512 and truncation is active, so the two runs differ at truncation level;
       --oracle also runs the CPU restatement (more than 20 minutes on 8 cores at this size).
-  C5  53-qubit Sycamore-style depth-14 circuit (circuits.sycamore_grid, routed by the nearest-neighbour pass), amplitude of
-      |0...0>, norm, discarded weight (fidelity estimate) at the bond dimensions given by --chi5; the circuit is fed in
-      chunks so that a run exceeding --budget seconds stops and says how far it got.
+  C5  the reference's examples/sycamore/resources/sycamore_53_14_0.xasm (committed fixture, 53 qubits, 14 cycles; 1897 NN 2q gates
+      after the nearest-neighbour pass), amplitude of |0...0>, norm, fidelity estimate prod(1 - w) at the bond dimensions given
+      by --chi5; the circuit is fed in chunks so that a run exceeding --budget seconds stops and says how far it got.
+  --gpus N shards the sites over N GPUs inside the library (mps_create_sharded).
 
 usage (GPU box): python scripts/configs_fullsize.py --which c3,c5 --chi5 256,512,1024 --budget 240 --out gpurun_out/rNN/configs.jsonl
 """
@@ -42,7 +43,7 @@ def run_c3(args):
     zz_by_mode = {}
     modes = [int(x) for x in args.fuse3.split(",")]
     for fuse in modes:
-        e = tnqvm_b200.B200MPS(n, max_bond=chi, fuse_2q=fuse)
+        e = tnqvm_b200.B200MPS(n, max_bond=chi, fuse_2q=fuse, devices=list(range(args.gpus)))
         e.run(cc); e.sync(); e.reset()          # warm-up: workspace, site buffers, pinned staging at their final sizes
         s0 = e.stats()
         t0 = time.perf_counter()
@@ -53,7 +54,7 @@ def run_c3(args):
         t_obs = time.perf_counter() - t0
         s1 = e.stats()
         zz_by_mode[fuse] = zz
-        emit(args.out, {"config": "c3_qaoa_ring", "qubits": n, "p": p, "max_bond_dim": chi, "fuse_2q": fuse, "gates_1q": n1, "gates_2q_nn": n2,
+        emit(args.out, {"config": "c3_qaoa_ring", "gpus": args.gpus, "site_blocks": e.shard_layout(), "boundary_exchanges": s1["boundary_exchanges"] - s0["boundary_exchanges"], "qubits": n, "p": p, "max_bond_dim": chi, "fuse_2q": fuse, "gates_1q": n1, "gates_2q_nn": n2,
                         "gates_2q_executed": s1["gates_2q"] - s0["gates_2q"], "gates_2q_fused": s1["gates_2q_fused"] - s0["gates_2q_fused"],
                         "run_ms": 1e3 * t_run, "nn_gates_2q_per_s": n2 / t_run, "zz_100_edges_ms": 1e3 * t_obs,
                         "energy": float(((1 - zz) / 2).sum()), "norm": e.norm(), "max_bond_reached": int(e.bond_dims().max()),
@@ -74,13 +75,13 @@ def run_c3(args):
 
 
 def run_c5(args):
-    n = 53
-    circ = Cc.nearest_neighbor(Cc.sycamore_grid(depth=args.depth5))
+    n, raw = Cc.sycamore_53(args.depth5)
+    circ = Cc.nearest_neighbor(raw)
     n1, n2 = Cc.count_gates(circ)
     chunk = args.chunk   # instructions per ABI call; large, so that the dependency layers keep their natural width
     for chi in [int(x) for x in args.chi5.split(",") if x]:
         for fuse in ([0, 1] if chi <= args.fuse_both_upto else [args.fuse5]):
-            e = tnqvm_b200.B200MPS(n, max_bond=chi, fuse_2q=fuse)
+            e = tnqvm_b200.B200MPS(n, max_bond=chi, fuse_2q=fuse, devices=list(range(args.gpus)))
             t0 = time.perf_counter()
             done2 = 0
             complete = True
@@ -93,7 +94,8 @@ def run_c5(args):
                     break
             t_run = time.perf_counter() - t0
             s = e.stats()
-            rec = {"config": "c5_sycamore_grid", "qubits": n, "depth": args.depth5, "max_bond_dim": chi, "fuse_2q": fuse, "gates_1q": n1, "gates_2q_nn": n2,
+            rec = {"config": "c5_sycamore_53_14_0", "gpus": args.gpus, "site_blocks": e.shard_layout(), "boundary_exchanges": s["boundary_exchanges"],
+                   "svd_nonconverged": s["svd_nonconverged"], "norm_guard_violations": s["norm_guard_violations"], "qubits": n, "depth": args.depth5, "max_bond_dim": chi, "fuse_2q": fuse, "gates_1q": n1, "gates_2q_nn": n2,
                    "complete": complete, "gates_2q_nn_done": done2, "gates_2q_executed": s["gates_2q"], "gates_2q_fused": s["gates_2q_fused"],
                    "run_s": t_run, "nn_gates_2q_per_s": done2 / t_run, "max_bond_reached": int(e.bond_dims().max()),
                    "bonds_at_max": int((e.bond_dims() >= chi).sum()), "jacobi_sweeps": s["jacobi_sweeps"], "launches": s["launches"]}
@@ -103,9 +105,9 @@ def run_c5(args):
                 rec.update({"amp0_re": amp.real, "amp0_im": amp.imag, "amp0_abs2_times_2^53": abs(amp) ** 2 * 2.0 ** n, "amp_ms": 1e3 * (time.perf_counter() - t0)})
                 nrm = e.norm()
                 dw = e.discarded_weight()
-                # no renormalisation in the reference gauge: <psi|psi> is the product of the kept weights, i.e. the usual
-                # MPS fidelity estimate; the sum of discarded weights gives the same number to first order
-                rec.update({"norm": nrm, "discarded_weight_sum": dw, "fidelity_estimate_norm": nrm})
+                # fidelity estimate of the truncated run: prod over truncations of (1 - discarded / total weight); the norm is a
+                # different quantity (the reference gauge is never renormalised nor canonical)
+                rec.update({"norm": nrm, "discarded_weight_sum": dw, "fidelity_estimate": e.fidelity_estimate()})
             emit(args.out, rec)
             e.close()
 
@@ -124,6 +126,7 @@ if __name__ == "__main__":
     ap.add_argument("--budget", type=float, default=240.0)
     ap.add_argument("--chunk", type=int, default=512)
     ap.add_argument("--out", default="")
+    ap.add_argument("--gpus", type=int, default=1)
     a = ap.parse_args()
     if "c3" in a.which:
         run_c3(a)

@@ -106,3 +106,24 @@ def test_sycamore_grid_stand_in_has_the_shape_of_the_resource_file():
     assert Cc.count_gates(nn) == (1240, 2200)
     assert all(abs(g[1][0] - g[1][1]) == 1 for g in nn if len(g[1]) == 2)
     assert Cc.sycamore_grid(seed=0) == c and Cc.sycamore_grid(seed=1) != c
+
+
+def test_plugin_activator_registers_the_visitor_service():
+    """tnqvm_b200/csrc/visitor/plugin/: the CppMicroServices activator (pattern of ExaTnMpsActivator.cpp:14-19), compiled against the
+    in-tree shim by build(), registers exactly one tnqvm::TNQVMVisitor named "exatn-mps"; manifest.json names the bundle; the
+    plugin CMakeLists.txt configures (XACC's CMake functions and targets stubbed)."""
+    import json
+    import shutil
+    import subprocess
+    import tempfile
+    plug = os.path.join(ROOT, "tnqvm_b200", "csrc", "visitor", "plugin")
+    exe = os.path.join(ROOT, "tnqvm_b200", "lib", "b200_activator_check")
+    assert os.path.exists(exe), "run build() first"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "name=exatn-mps" in r.stdout, r.stdout + r.stderr
+    man = json.load(open(os.path.join(plug, "manifest.json")))
+    assert man["bundle.symbolic_name"] == "tnqvm_b200_mps" and man["bundle.activator"] is True
+    if shutil.which("cmake"):
+        with tempfile.TemporaryDirectory() as tmp:
+            c = subprocess.run(["cmake", "-S", os.path.join(plug, "cmake_check"), "-B", tmp, "-DMPS_B200_ROOT=" + ROOT], capture_output=True, text=True, timeout=300)
+            assert c.returncode == 0, c.stdout[-1500:] + c.stderr[-1500:]

@@ -209,6 +209,34 @@ def test_sampling_large_register_ghz35(O):
     e.close()
 
 
+def test_sampling_large_register_many_shots_all_qubits(O):
+    """n >= 20 sampler with cached environments: 1000 shots x 35 measured qubits on GHZ-35, the strings
+    equal the oracle's (same mt19937_64 stream, same draw order, getMeasureSample :2211-2364) -- ascending, descending and
+    scattered Measure orders, a qubit measured twice included -- and the ascending run takes about a second."""
+    import time
+    base = [g for g in RC.ghz35() if g[0] != "Measure"]
+    for order, shots in ((list(range(35)), 1000), (list(range(34, -1, -1)), 40), ([5, 3, 7, 34, 3, 20], 60)):
+        circ = base + [("Measure", (q,), ()) for q in order]
+        e = gpu_run(35, circ, seed=11)
+        t0 = time.perf_counter()
+        got = e.sample_strings(shots, len(order))
+        dt = time.perf_counter() - t0
+        e.close()
+        o = O.OracleMPS(35, seed=11).run(circ)
+        assert got == o.sample(shots, len(order)), order[:4]
+        assert set(s[0] * len(order) for s in got) == set(got)   # GHZ: all measured bits agree
+        if shots == 1000:
+            assert dt < 3.0, dt   # measured ~1 s on B200 (reference algorithm: 70 full-chain contractions per shot)
+            print("GHZ-35, 1000 shots x 35 qubits: %.2f s" % dt)
+    # a state with bond dimension > 2 and non-trivial conditionals
+    n = 22
+    circ = Cc.brickwork(n, 6, seed=13) + [("Measure", (q,), ()) for q in (0, 4, 5, 11, 21, 10)]
+    e = gpu_run(n, circ, seed=3, max_bond=8)
+    o = O.OracleMPS(n, seed=3, max_bond=8, null_tol=engine_null_tol(8)).run(circ)
+    assert e.sample_strings(200, 6) == o.sample(200, 6)
+    e.close()
+
+
 def test_edge_registers_and_errors():
     e = tnqvm_b200.B200MPS(1)
     e.apply("X", (0,))
@@ -523,10 +551,11 @@ def teacher_forced_parity(O, n, circ, chi, layer_pick=lambda i: True, tol=1e-10)
             ko = Ao.shape[2]
             kk = max(keep, ko)
             gap = (sv[min(keep, ko) - 1] - sv[kk]) / sv[0] if kk < len(sv) else 1.0
-            if gap > 1e-9:   # subspace perturbation ~ rounding / gap
+            tail_null = kk >= len(sv) or sv[kk] <= 1e-10 * sv[0]   # nothing of weight is discarded: the product is theta itself
+            if tail_null or gap > 1e-9:   # subspace perturbation ~ rounding / gap
                 dp = np.abs(Pe - Po).max() / sv[0]
                 worst["dprod"] = max(worst["dprod"], dp)
-                assert dp < max(tol, 1e-13 / gap), (li, g, dp, gap)
+                assert dp < (tol if tail_null else max(tol, 1e-13 / gap)), (li, g, dp, gap)
             else:
                 degenerate += 1
             checked += 1

@@ -149,3 +149,21 @@ def test_visitor_vqe_mode_one_ansatz_many_terms():
     sv = np.array([complex(a, b) for a, b in res["state"]])
     sv0 = np.array([complex(a, b) for a, b in base["state"]])
     assert np.abs(sv - sv0).max() < 1e-12
+
+
+@pytest.mark.gpu
+def test_visitor_execution_info_has_the_reference_stat_buckets():
+    """getExecutionInfo() carries the reference's per-phase statistics under the reference's names (FunctionCallStat buckets,
+    ExatnUtils.hpp:57-126; ExaTnMpsVisitor.cpp:345, 680, 1292, 1523, 1626, 1718, 1729) plus the engine counters; with
+    "b200-profile" the three GPU phases of the two-qubit step are timed with CUDA events."""
+    n = 12
+    circ = Cc.brickwork(n, 6, seed=2)
+    doc = json.loads(run(circ, n, "--max-bond-dim", 16, "--profile").strip().splitlines()[-1])
+    info = doc["execution_info"]
+    n1, n2 = Cc.count_gates(circ)
+    assert info["Initialize [calls]"] == 1 and info["Finalize [calls]"] == 1
+    assert info["One-qubit Gate Total [calls]"] == n1 and info["Two-qubit Gate Total [calls]"] == n2
+    for key in ("Contract Two-Qubit Gate Tensor [secs]", "Decompose Tensor SVD [secs]", "Truncate SVD Tensor [secs]"):
+        assert info[key] > 0.0, key
+    assert info["Two-qubit Gate Total [gpu gates]"] == n2 and info["b200-kernel-launches"] > 0
+    assert info["b200-svd-nonconverged"] == 0

@@ -30,6 +30,8 @@
 #include <unistd.h>
 #include <cstdlib>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges show up in Nsight Systems / Compute timelines, no-ops otherwise
+
 #include "../../include/mps_b200.h"
 #include "kernels.h"
 
@@ -45,6 +47,12 @@ typedef std::complex<double> cplx;
   } while (0)
 
 namespace {
+
+// NVTX range over a scope: the phases of the two-qubit step carry the reference's stat bucket names
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct SiteBuf {
   double2* d = nullptr;
@@ -171,6 +179,8 @@ struct mps_b200_handle {
   size_t pin_rb_cap = 0;
   cudaEvent_t ev[6] = {};
   cudaEvent_t sev[2] = {};   // Jacobi sweep read-backs (the host runs one sweep behind the device)
+  cudaStream_t stream2 = nullptr;   // right-to-left environment sweep of the observables, concurrent with the left-to-right one
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   int sm_count = 148;
   // persistent sweep kernel: resident CTAs per SM.  0 = by load: the routed circuits (configs 3 and 5) run layers of 2-8
   // gates, i.e. fewer pair tasks per tournament step than SMs x 4; launching only as many CTAs as there are tasks keeps
@@ -606,12 +616,16 @@ struct mps_b200_handle {
     int* d_rem = d_done + B;   // per chunk c: d_rem[2c] = matrices still rotating, d_rem[2c+1] = dataflow faults
     double* d_fro2 = (double*)(wb + oFlags + ((sizeof(int) * (4 * B + 4) + 7) & ~size_t(7)));
 
+    NvtxRange nvtx_layer("mps_b200: Two-qubit Gate layer");
     if (profile) CK(cudaEventRecord(ev[0], stream));
+    nvtxRangePushA("Contract Two-Qubit Gate Tensor (theta GEMM + gate)");
     launch_gemm((const GemmProblem*)(wb + oGemm), B, max_tiles, 0, stream);
+    nvtxRangePop();
     nlaunch += 1;
     if (profile) CK(cudaEventRecord(ev[1], stream));
 
     // ---- QR pre-reduction: theta_o = Q R, the Jacobi runs on G = R^H
+    nvtxRangePushA("Decompose Tensor SVD (QR pre-reduction + Jacobi sweeps)");
     if (use_qr) {
       launch_qr((const QrProblem*)(wb + oQr), B, maxMg, maxNg, stream);
       nlaunch += qr_launch_count(maxNg);
@@ -729,6 +743,8 @@ struct mps_b200_handle {
     if (profile) CK(cudaEventRecord(ev[2], stream));
 
     // ---- sort / truncate, read back kept dims + singular values
+    nvtxRangePop();
+    nvtxRangePushA("Truncate SVD Tensor (sort, cut rule, write-back)");
     launch_trunc((const TruncProblem*)(wb + oTr), B, cutoff, cutoff_on_sqrt, max_bond, gauge, renorm, ntol, stream);
     nlaunch += 1;
     const size_t keepBlkBytes = ((sizeof(int) * B + 15) & ~size_t(15)) + 2 * sizeof(double) * B;
@@ -830,6 +846,7 @@ struct mps_b200_handle {
     launch_gather((const GatherProblem*)(wb + oGat), B, max_rows, max_keep, stream);
     launch_gemm((const GemmProblem*)(wb + oGemm2), B, max_tiles2, use_qr ? 0 : 1, stream);
     nlaunch += 2;
+    nvtxRangePop();
     CK(cudaGetLastError());
     if (profile) {
       CK(cudaEventRecord(ev[3], stream));
@@ -848,7 +865,8 @@ struct mps_b200_handle {
   // If envs != nullptr the environment before each site is kept there (device pointers into the arena).
   struct EnvBufs { std::vector<double2*> e; };
 
-  void left_step(const SiteBuf& S, const double2* E, double2* F, double2* Eout, double w0, double w1) {
+  void left_step(const SiteBuf& S, const double2* E, double2* F, double2* Eout, double w0, double w1, cudaStream_t st_ = nullptr) {
+    cudaStream_t stream = st_ ? st_ : this->stream;   // shadows the member: every launch below goes to the chosen stream
     const int dl = S.dl, dr = S.dr;
     if (w0 == w1) {
       // both physical slices in one GEMM: the site is a column-major dl x (2 dr) matrix with column index p + 2c
@@ -874,9 +892,20 @@ struct mps_b200_handle {
     nlaunch += (w0 == w1) ? 1 : 3;
   }
   // R_k[a,a'] = sum_{p,c,c'} A[a,p,c] R[c,c'] conj(A[a',p,c'])
-  void right_step(const SiteBuf& S, const double2* R, double2* H, double2* Rout) {
+  void right_step(const SiteBuf& S, const double2* R, double2* H, double2* Rout, cudaStream_t st_ = nullptr, double w0 = 1.0, double w1 = 1.0) {
+    cudaStream_t stream = st_ ? st_ : this->stream;
     const int dl = S.dl, dr = S.dr;
-    {
+    if (w0 != 1.0 || w1 != 1.0) {
+      // H_p = w_p S_p R, one GEMM per physical slice
+      for (int p = 0; p < 2; ++p) {
+        GemmProblem g;
+        memset(&g, 0, sizeof(g));
+        g.A = S.d + (size_t)p * dl; g.lda = 2 * dl; g.B = R; g.ldb = dr; g.C = H + (size_t)p * dl; g.ldc = 2 * dl;
+        g.M = dl; g.N = dr; g.K = dr; g.b_col_stride = 1; g.alpha = p ? w1 : w0;
+        launch_gemm1(g, 0, stream);
+      }
+      nlaunch += 1;
+    } else {
       // H[(a,p), c'] = sum_c S[(a,p), c] R[c, c']: the site as a (2 dl) x dr matrix, both physical slices in one GEMM
       GemmProblem g;
       memset(&g, 0, sizeof(g));
@@ -927,7 +956,7 @@ struct mps_b200_handle {
   }
 
   // left environments L[k] (before site s0+k, k = 0..n) and right environments R[k] (after site s0+k-1)
-  void build_envs(int reg, std::vector<double2*>& Lv, std::vector<double2*>& Rv, double2*& F, double2*& Etmp, double2*& Etmp2, double2*& scal) {
+  void build_envs(int reg, std::vector<double2*>& Lv, std::vector<double2*>& Rv, double2*& F, double2*& Etmp, double2*& Etmp2, double2*& scal, int nscal = 0) {
     flush();
     const int s0 = reg * nq, n = nq;
     ws.reset();
@@ -938,60 +967,82 @@ struct mps_b200_handle {
       oR[k] = ws.reserve(d * d * 16);
     }
     const size_t oF = ws.reserve(max_site_elems(s0, s0 + n) * 16);
+    const size_t oF2 = ws.reserve(max_site_elems(s0, s0 + n) * 16);
     const size_t oT = ws.reserve(max_env_elems(s0, s0 + n) * 16);
     const size_t oT2 = ws.reserve(max_env_elems(s0, s0 + n) * 16);
-    const size_t oS = ws.reserve(16 * (size_t)(n + 8));
+    const size_t oS = ws.reserve(16 * (size_t)(n + 8 + nscal));
     ensure_ws(ws.off);
     Lv.resize(n + 1); Rv.resize(n + 1);
     for (int k = 0; k <= n; ++k) { Lv[k] = (double2*)(ws.base + oL[k]); Rv[k] = (double2*)(ws.base + oR[k]); }
     F = (double2*)(ws.base + oF);
+    double2* F2 = (double2*)(ws.base + oF2);
     Etmp = (double2*)(ws.base + oT);
     Etmp2 = (double2*)(ws.base + oT2);
     scal = (double2*)(ws.base + oS);
     const cplx one(1, 0);
     CK(cudaMemcpyAsync(Lv[0], &one, 16, cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(Rv[n], &one, 16, cudaMemcpyHostToDevice, stream));
+    // the two environment chains are independent: left-to-right on the handle's stream, right-to-left on the second one
+    CK(cudaEventRecord(fork_ev, stream));
+    CK(cudaStreamWaitEvent(stream2, fork_ev, 0));
     for (int k = 0; k < n; ++k) left_step(sites[s0 + k], Lv[k], F, Lv[k + 1], 1.0, 1.0);
-    for (int k = n - 1; k >= 0; --k) right_step(sites[s0 + k], Rv[k + 1], F, Rv[k]);
+    for (int k = n - 1; k >= 0; --k) right_step(sites[s0 + k], Rv[k + 1], F2, Rv[k], stream2);
+    CK(cudaEventRecord(join_ev, stream2));
+    CK(cudaStreamWaitEvent(stream, join_ev, 0));
   }
 
   // <Z_k> for every k and the norm from ONE left and ONE right transfer sweep: the left sweep keeps F_k = L_k S_k, the
-  // right sweep forms H_k = S_k R_{k+1}, and <psi| Z_k |psi> = sum_{a,p,c} (-1)^p conj(F_k[a,p,c]) H_k[a,p,c]
-  // (L_k is Hermitian).  4 GEMMs + one reduction per site instead of 9 GEMMs.
+  // right sweep keeps H_k = S_k R_{k+1}, and <psi| Z_k |psi> = sum_{a,p,c} (-1)^p conj(F_k[a,p,c]) H_k[a,p,c]
+  // (L_k is Hermitian).  The two sweeps are independent chains of small GEMMs (latency-bound along the chain), so they run
+  // concurrently on two streams; all n reductions are then ONE batched multi-CTA launch and one read-back.
   void expval_z_all(int reg, double* out) {
     flush();
     const int s0 = reg * nq, n = nq;
     ws.reset();
-    std::vector<size_t> oF(n);
+    std::vector<size_t> oF(n), oHk(n);
     size_t maxL = 1;
     for (int k = 0; k < n; ++k) {
-      oF[k] = ws.reserve((size_t)2 * sites[s0 + k].dl * sites[s0 + k].dr * 16);
+      const size_t bytes = (size_t)2 * sites[s0 + k].dl * sites[s0 + k].dr * 16;
+      oF[k] = ws.reserve(bytes);
+      oHk[k] = ws.reserve(bytes);
       maxL = std::max(maxL, (size_t)sites[s0 + k].dr * sites[s0 + k].dr);
     }
-    const size_t oE0 = ws.reserve(maxL * 16), oE1 = ws.reserve(maxL * 16);
-    const size_t oH = ws.reserve(max_site_elems(s0, s0 + n) * 16);
+    constexpr int DOT_CTAS = 32;
+    const size_t oE0 = ws.reserve(maxL * 16), oE1 = ws.reserve(maxL * 16), oR0 = ws.reserve(maxL * 16), oR1 = ws.reserve(maxL * 16);
     const size_t oS = ws.reserve(16 * (size_t)(n + 8));
+    const size_t oP = ws.reserve(sizeof(DotProblem) * (size_t)n);
+    const size_t oPart = ws.reserve(16 * (size_t)n * DOT_CTAS);
     ensure_ws(ws.off);
     double2* E[2] = {(double2*)(ws.base + oE0), (double2*)(ws.base + oE1)};
-    double2* H = (double2*)(ws.base + oH);
+    double2* R[2] = {(double2*)(ws.base + oR0), (double2*)(ws.base + oR1)};
     double2* scal = (double2*)(ws.base + oS);
     const cplx one(1, 0);
     CK(cudaMemcpyAsync(E[0], &one, 16, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(R[0], &one, 16, cudaMemcpyHostToDevice, stream));
+    std::vector<DotProblem> hp(n);
+    for (int k = 0; k < n; ++k) {
+      const SiteBuf& S = sites[s0 + k];
+      hp[k].F = (const double2*)(ws.base + oF[k]); hp[k].H = (const double2*)(ws.base + oHk[k]);
+      hp[k].total = 2L * S.dl * S.dr; hp[k].n = S.dl; hp[k].mode = 0; hp[k].w0 = 1.0; hp[k].w1 = -1.0;
+    }
+    CK(cudaMemcpyAsync(ws.base + oP, hp.data(), sizeof(DotProblem) * (size_t)n, cudaMemcpyHostToDevice, stream));   // pageable source: staged before the call returns
+    CK(cudaEventRecord(fork_ev, stream));
+    CK(cudaStreamWaitEvent(stream2, fork_ev, 0));
     int cur = 0;
     for (int k = 0; k < n; ++k) {
       left_step(sites[s0 + k], E[cur], (double2*)(ws.base + oF[k]), E[cur ^ 1], 1.0, 1.0);
       cur ^= 1;
     }
     CK(cudaMemcpyAsync(scal + n, E[cur], 16, cudaMemcpyDeviceToDevice, stream));   // <psi|psi>
-    CK(cudaMemcpyAsync(E[0], &one, 16, cudaMemcpyHostToDevice, stream));
-    cur = 0;
+    int rc = 0;
     for (int k = n - 1; k >= 0; --k) {
-      const SiteBuf& S = sites[s0 + k];
-      right_step(S, E[cur], H, E[cur ^ 1]);
-      launch_site_dot((const double2*)(ws.base + oF[k]), H, S.dl, S.dr, 1.0, -1.0, scal + k, stream);
-      nlaunch += 1;
-      cur ^= 1;
+      right_step(sites[s0 + k], R[rc], (double2*)(ws.base + oHk[k]), R[rc ^ 1], stream2);
+      rc ^= 1;
     }
+    CK(cudaEventRecord(join_ev, stream2));
+    CK(cudaStreamWaitEvent(stream, join_ev, 0));
+    launch_dot_batch((const DotProblem*)(ws.base + oP), n, DOT_CTAS, (double2*)(ws.base + oPart), scal, stream);
+    nlaunch += 2;
     std::vector<cplx> h(n + 1);
     CK(cudaMemcpyAsync(h.data(), scal, 16 * (size_t)(n + 1), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
@@ -1004,29 +1055,154 @@ struct mps_b200_handle {
   void expval_zz_pairs(int reg, int np, const int* qi, const int* qj, double* out) {
     std::vector<double2*> Lv, Rv;
     double2 *F, *Et, *Et2, *scal;
-    build_envs(reg, Lv, Rv, F, Et, Et2, scal);
+    for (int t = 0; t < np; ++t)
+      if (std::min(qi[t], qj[t]) < 0 || std::max(qi[t], qj[t]) >= nq) throw std::runtime_error("qubit index out of range");
+    build_envs(reg, Lv, Rv, F, Et, Et2, scal, np);
     const int s0 = reg * nq;
-    std::vector<cplx> h(1);
     for (int t = 0; t < np; ++t) {
-      int i = std::min(qi[t], qj[t]), j = std::max(qi[t], qj[t]);
-      if (i < 0 || j >= nq) throw std::runtime_error("qubit index out of range");
-      const double2* src;
-      int dlast;
-      if (i == j) { src = Lv[nq]; dlast = 1; launch_trace_pair(src, Rv[nq], 1, scal, stream); }
+      const int i = std::min(qi[t], qj[t]), j = std::max(qi[t], qj[t]);
+      if (i == j) launch_trace_pair(Lv[nq], Rv[nq], 1, scal + t, stream);
       else {
         left_step(sites[s0 + i], Lv[i], F, Et, 1.0, -1.0);
         double2* cur = Et; double2* nxt = Et2;
         for (int k = i + 1; k < j; ++k) { left_step(sites[s0 + k], cur, F, nxt, 1.0, 1.0); std::swap(cur, nxt); }
         left_step(sites[s0 + j], cur, F, nxt, 1.0, -1.0);
-        dlast = sites[s0 + j].dr;
-        launch_trace_pair(nxt, Rv[j + 1], dlast, scal, stream);
+        launch_trace_pair(nxt, Rv[j + 1], sites[s0 + j].dr, scal + t, stream);
       }
       nlaunch += 1;
-      CK(cudaMemcpyAsync(h.data(), scal, 16, cudaMemcpyDeviceToHost, stream));
-      CK(cudaStreamSynchronize(stream));
-      out[t] = h[0].real();
+    }
+    std::vector<cplx> h(np);   // ONE read-back for all pairs
+    CK(cudaMemcpyAsync(h.data(), scal, 16 * (size_t)np, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    for (int t = 0; t < np; ++t) out[t] = h[t].real();
+  }
+
+  // getMeasureSample (ExaTnMpsVisitor.cpp:2211-2364) for registers of 20 qubits and more: per shot, the measured qubits in
+  // Measure order; for each one the diagonal of its reduced density matrix conditioned on the outcomes so far, one uniform
+  // draw, 0 iff r <= p0 (:2329-2345).  The reference contracts the whole <psi|psi> ladder for every measured qubit of every shot.
+  // Here the unconditioned left / right environments are built once; a shot only re-propagates the environments its own
+  // projectors invalidate (measuring in ascending qubit order: ONE transfer step per qubit, and H_q = S_q R_{q+1} is shared by
+  // all shots).  p_b = sum conj(F_b) H_b with F = L_q S_q, H = S_q R_{q+1}.  Same draws in the same order as the reference.
+  int sample_rdm(int reg, int shots, char* out) {
+    flush();
+    const int s0 = reg * nq, n = nq, nm = (int)measure.size();
+    ws.reset();
+    std::vector<size_t> oL0(n + 1), oR0(n + 1), oLc(n + 1), oRc(n + 1), oHb(n);
+    for (int k = 0; k <= n; ++k) {
+      const size_t d = (k == 0) ? 1 : sites[s0 + k - 1].dr;
+      oL0[k] = ws.reserve(d * d * 16); oR0[k] = ws.reserve(d * d * 16);
+      oLc[k] = ws.reserve(d * d * 16); oRc[k] = ws.reserve(d * d * 16);
+    }
+    std::vector<char> is_meas(n, 0);
+    for (int q : measure) is_meas[q] = 1;
+    for (int k = 0; k < n; ++k) oHb[k] = is_meas[k] ? ws.reserve((size_t)2 * sites[s0 + k].dl * sites[s0 + k].dr * 16) : 0;
+    const size_t site_max = max_site_elems(s0, s0 + n) * 16;
+    const size_t oF = ws.reserve(site_max), oF2 = ws.reserve(site_max), oH = ws.reserve(site_max);
+    constexpr int DOT_CTAS = 16;
+    const size_t oP = ws.reserve(sizeof(DotProblem) * (size_t)(4 * n));
+    const size_t oPart = ws.reserve(16 * 2 * DOT_CTAS);
+    const size_t oS = ws.reserve(64);
+    ensure_ws(ws.off);
+    auto env = [&](const std::vector<size_t>& o, int k) { return (double2*)(ws.base + o[k]); };
+    double2* F = (double2*)(ws.base + oF);
+    double2* F2 = (double2*)(ws.base + oF2);
+    double2* Hs = (double2*)(ws.base + oH);
+    double2* scal = (double2*)(ws.base + oS);
+    const cplx one(1, 0);
+    CK(cudaMemcpyAsync(env(oL0, 0), &one, 16, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(env(oR0, n), &one, 16, cudaMemcpyHostToDevice, stream));
+    // dot descriptors: per site (p0, p1) against the shared H_q and against the per-shot scratch H
+    std::vector<DotProblem> hp(4 * (size_t)n);
+    for (int k = 0; k < n; ++k)
+      for (int v = 0; v < 2; ++v)
+        for (int b = 0; b < 2; ++b) {
+          DotProblem& d = hp[4 * k + 2 * v + b];
+          d.F = F; d.H = v ? Hs : (double2*)(ws.base + oHb[k]);
+          d.total = 2L * sites[s0 + k].dl * sites[s0 + k].dr; d.n = sites[s0 + k].dl; d.mode = 0;
+          d.w0 = b ? 0.0 : 1.0; d.w1 = b ? 1.0 : 0.0;
+        }
+    CK(cudaMemcpyAsync(ws.base + oP, hp.data(), sizeof(DotProblem) * hp.size(), cudaMemcpyHostToDevice, stream));
+    // unconditioned environments (two concurrent chains); the right chain also leaves H_q = S_q R_{q+1} for the measured sites
+    CK(cudaEventRecord(fork_ev, stream));
+    CK(cudaStreamWaitEvent(stream2, fork_ev, 0));
+    for (int k = 0; k < n; ++k) left_step(sites[s0 + k], env(oL0, k), F, env(oL0, k + 1), 1.0, 1.0);
+    for (int k = n - 1; k >= 0; --k)
+      right_step(sites[s0 + k], env(oR0, k + 1), is_meas[k] ? (double2*)(ws.base + oHb[k]) : F2, env(oR0, k), stream2);
+    CK(cudaEventRecord(join_ev, stream2));
+    CK(cudaStreamWaitEvent(stream, join_ev, 0));
+
+    std::vector<const double2*> curL(n + 1), curR(n + 1);
+    std::vector<std::array<double, 2>> w(n);
+    cplx* h2 = (cplx*)pinned_rb(64);   // pinned: the two probabilities come back without a staging copy
+    const double PROB_EPS = 1e-12;
+    for (int s = 0; s < shots; ++s) {
+      for (int k = 0; k <= n; ++k) { curL[k] = env(oL0, k); curR[k] = env(oR0, k); }
+      std::fill(w.begin(), w.end(), std::array<double, 2>{1.0, 1.0});
+      int Lvalid = n, Rvalid = 0;   // curL[0..Lvalid] and curR[Rvalid..n] are consistent with the projectors set so far
+      for (int mi = 0; mi < nm; ++mi) {
+        const int q = measure[mi];
+        const SiteBuf& S = sites[s0 + q];
+        for (int k = Lvalid; k < q; ++k) {
+          left_step(sites[s0 + k], curL[k], F, env(oLc, k + 1), w[k][0], w[k][1]);
+          curL[k + 1] = env(oLc, k + 1);
+        }
+        Lvalid = std::max(Lvalid, q);
+        for (int k = Rvalid - 1; k > q; --k) {
+          right_step(sites[s0 + k], curR[k + 1], F2, env(oRc, k), nullptr, w[k][0], w[k][1]);
+          curR[k] = env(oRc, k);
+        }
+        Rvalid = std::min(Rvalid, q + 1);
+        const bool shared_h = (curR[q + 1] == env(oR0, q + 1)) && w[q][0] == 1.0 && w[q][1] == 1.0;
+        {   // F = L_q S_q (both physical slices in one GEMM)
+          GemmProblem g;
+          memset(&g, 0, sizeof(g));
+          g.A = curL[q]; g.lda = S.dl; g.B = S.d; g.ldb = S.dl; g.C = F; g.ldc = S.dl;
+          g.M = S.dl; g.N = 2 * S.dr; g.K = S.dl; g.b_col_stride = 1; g.alpha = 1.0;
+          launch_gemm1(g, 0, stream);
+          nlaunch += 1;
+        }
+        if (!shared_h) {   // H = S_q R_{q+1} under this shot's projectors
+          GemmProblem g;
+          memset(&g, 0, sizeof(g));
+          g.A = S.d; g.lda = 2 * S.dl; g.B = curR[q + 1]; g.ldb = S.dr; g.C = Hs; g.ldc = 2 * S.dl;
+          g.M = 2 * S.dl; g.N = S.dr; g.K = S.dr; g.b_col_stride = 1; g.alpha = 1.0;
+          launch_gemm1(g, 0, stream);
+          nlaunch += 1;
+        }
+        const long tot = 2L * S.dl * S.dr;
+        launch_dot_batch((const DotProblem*)(ws.base + oP) + 4 * q + (shared_h ? 0 : 2), 2, (int)std::max<long>(1, std::min<long>(DOT_CTAS, tot / 2048)),
+                         (double2*)(ws.base + oPart), scal, stream);
+        nlaunch += 2;
+        CK(cudaMemcpyAsync(h2, scal, 32, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        // a qubit measured twice: its earlier projector is part of w[q]
+        const double pb0 = h2[0].real() * w[q][0], pb1 = h2[1].real() * w[q][1];
+        const double p0 = std::fabs(pb0) < PROB_EPS ? 0.0 : pb0;
+        const double p1 = std::fabs(pb1) < PROB_EPS ? 0.0 : pb1;
+        const double r = std::uniform_real_distribution<double>(0.0, 1.0)(rng);
+        const int bit = (r <= p0) ? 0 : 1;
+        const double pr = bit == 0 ? p0 : p1;
+        w[q][bit] *= 1.0 / pr;
+        w[q][1 - bit] = 0.0;
+        out[(size_t)s * nm + mi] = bit ? '1' : '0';
+        // the projector invalidates the conditioned environments on both sides of q; the left one is extended right away from
+        // the F just computed:  L_{q+1} = w_b S_b^H F_b
+        if (std::isfinite(w[q][bit])) {
+          GemmProblem g;
+          memset(&g, 0, sizeof(g));
+          g.A = S.d + (size_t)bit * S.dl; g.lda = 2 * S.dl; g.B = F + (size_t)bit * S.dl; g.ldb = 2 * S.dl; g.C = env(oLc, q + 1); g.ldc = S.dr;
+          g.M = S.dr; g.N = S.dr; g.K = S.dl; g.b_col_stride = 1; g.alpha = w[q][bit];
+          launch_gemm1(g, 1, stream);
+          nlaunch += 1;
+          curL[q + 1] = env(oLc, q + 1);
+          Lvalid = q + 1;
+        } else Lvalid = std::min(Lvalid, q);
+        Rvalid = std::max(Rvalid, q + 1);
+      }
     }
     CK(cudaGetLastError());
+    return shots;
   }
 
   // amplitudes with open legs: bits[k] in {0,1,-1}
@@ -1328,6 +1504,9 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
     }
     for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
     for (auto& ev : h->sev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
     {
       // persisting-L2 carve-out for the Jacobi work matrices (see run_layer); both limits are device properties
       h->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
@@ -1388,6 +1567,9 @@ int mps_destroy(mps_handle_t h) {
   if (h->pin_rb) cudaFreeHost(h->pin_rb);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->sev) if (ev) cudaEventDestroy(ev);
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  if (h->join_ev) cudaEventDestroy(h->join_ev);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -1661,34 +1843,7 @@ int mps_sample(mps_handle_t h, int reg, int shots, char* out, size_t out_cap, in
       }
       produced = (int)m;
     } else {
-      // getMeasureSample (ExaTnMpsVisitor.cpp:2211-2364): conditional single-qubit RDM diagonals in Measure order
-      for (int s = 0; s < shots; ++s) {
-        std::vector<int> res;
-        std::vector<double> probs;
-        for (int mi = 0; mi < nm; ++mi) {
-          const int q = e->measure[mi];
-          double pb[2];
-          for (int b = 0; b < 2; ++b) {
-            std::vector<std::array<double, 2>> w(e->nq, {1.0, 1.0});
-            for (size_t j = 0; j < res.size(); ++j) {
-              const int qq = e->measure[j];
-              w[qq][res[j]] *= 1.0 / probs[j];
-              w[qq][1 - res[j]] = 0.0;
-            }
-            w[q][1 - b] = 0.0;
-            pb[b] = e->sweep_weights(reg, w).real();
-          }
-          const double PROB_EPS = 1e-12;
-          const double p0 = std::fabs(pb[0]) < PROB_EPS ? 0.0 : pb[0];
-          const double p1 = std::fabs(pb[1]) < PROB_EPS ? 0.0 : pb[1];
-          const double r = std::uniform_real_distribution<double>(0.0, 1.0)(e->rng);
-          const int bit = (r <= p0) ? 0 : 1;
-          res.push_back(bit);
-          probs.push_back(bit == 0 ? p0 : p1);
-          out[(size_t)s * nm + mi] = bit ? '1' : '0';
-        }
-        ++produced;
-      }
+      produced = e->sample_rdm(reg, shots, out);
     }
   }
   if (n_out) *n_out = produced;

@@ -126,6 +126,16 @@ void launch_gate1q(const Gate1qProblem* d_probs, int batch, long max_elems, cuda
 void launch_trace_pair(const double2* E, const double2* R, int n, double2* out, cudaStream_t s);
 // out[0] = sum_{a,p,c} w_p conj(F[a,p,c]) H[a,p,c]  (site-shaped arrays (dl,2,dr), column-major)
 void launch_site_dot(const double2* F, const double2* H, int dl, int dr, double w0, double w1, double2* out, cudaStream_t s);
+// batched multi-CTA reductions of the observables (two launches, fixed summation order)
+struct DotProblem {
+  const double2* F;
+  const double2* H;
+  long total;      // elements of F
+  int n;           // mode 0: dl of the site-shaped pair (physical index = (e / dl) & 1); mode 1: order of the square environments
+  int mode;        // 0: sum w_p conj(F) H ; 1: sum_{i,j} F[i + n j] H[j + n i]
+  double w0, w1;
+};
+void launch_dot_batch(const DotProblem* d_probs, int nprob, int ctas_per_problem, double2* d_partial /* nprob x ctas */, double2* d_out, cudaStream_t s);
 void launch_fill(double2* p, long n, double2 v, cudaStream_t s);
 void launch_randn(double2* p, long n, uint64_t seed, cudaStream_t s);
 

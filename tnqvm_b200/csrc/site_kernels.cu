@@ -73,6 +73,45 @@ __global__ void __launch_bounds__(1024) site_dot_kernel(const double2* __restric
   if (threadIdx.x == 0) *out = make_double2(sr[0], si[0]);
 }
 
+// Batched, multi-CTA version of the two reductions above for the observables: problem b is either a weighted site dot
+// (mode 0: sum_e w_p(e) conj(F[e]) H[e] over a site-shaped pair) or an environment trace (mode 1: sum_{i,j} F[i + n j] H[j + n i]).
+// Stage 1: CTA (x, b) reduces a strided share into partial[b][x]; stage 2 sums the partials of a problem in a fixed order.
+__global__ void __launch_bounds__(256) dot_batch_partial_kernel(const DotProblem* __restrict__ probs, double2* __restrict__ partial) {
+  const DotProblem P = probs[blockIdx.y];
+  double re = 0.0, im = 0.0;
+  if (P.mode == 0) {
+    for (long e = (long)blockIdx.x * 256 + threadIdx.x; e < P.total; e += (long)gridDim.x * 256) {
+      const int p = (int)((e / P.n) & 1);
+      const double w = p ? P.w1 : P.w0;
+      const double2 a = P.F[e], b = P.H[e];
+      re += w * (a.x * b.x + a.y * b.y);
+      im += w * (a.x * b.y - a.y * b.x);
+    }
+  } else {
+    for (long e = (long)blockIdx.x * 256 + threadIdx.x; e < P.total; e += (long)gridDim.x * 256) {
+      const long j = e / P.n, i = e - j * P.n;
+      const double2 a = P.F[e], b = P.H[j + (long)P.n * i];
+      re += a.x * b.x - a.y * b.y;
+      im += a.x * b.y + a.y * b.x;
+    }
+  }
+  __shared__ double sr[256], si[256];
+  sr[threadIdx.x] = re; si[threadIdx.x] = im;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sr[threadIdx.x] += sr[threadIdx.x + o]; si[threadIdx.x] += si[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = make_double2(sr[0], si[0]);
+}
+__global__ void dot_batch_final_kernel(const double2* __restrict__ partial, int per_problem, int nprob, double2* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nprob) return;
+  double re = 0.0, im = 0.0;
+  for (int i = 0; i < per_problem; ++i) { const double2 v = partial[(size_t)b * per_problem + i]; re += v.x; im += v.y; }
+  out[b] = make_double2(re, im);
+}
+
 __global__ void fill_kernel(double2* p, long n, double2 v) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -107,6 +146,15 @@ void launch_trace_pair(const double2* E, const double2* R, int n, double2* out, 
 }
 void launch_site_dot(const double2* F, const double2* H, int dl, int dr, double w0, double w1, double2* out, cudaStream_t s) {
   site_dot_kernel<<<1, 1024, 0, s>>>(F, H, dl, dr, w0, w1, out);
+}
+void launch_dot_batch(const DotProblem* d_probs, int nprob, int ctas_per_problem, double2* d_partial, double2* d_out, cudaStream_t s) {
+  if (nprob <= 0) return;
+  if (ctas_per_problem == 1) {   // one CTA per problem: its "partial" is the result
+    dot_batch_partial_kernel<<<dim3(1, (unsigned)nprob), 256, 0, s>>>(d_probs, d_out);
+    return;
+  }
+  dot_batch_partial_kernel<<<dim3((unsigned)ctas_per_problem, (unsigned)nprob), 256, 0, s>>>(d_probs, d_partial);
+  dot_batch_final_kernel<<<(nprob + 127) / 128, 128, 0, s>>>(d_partial, ctas_per_problem, nprob, d_out);
 }
 void launch_fill(double2* p, long n, double2 v, cudaStream_t s) {
   if (n <= 0) return;

@@ -4,6 +4,8 @@
 //   finalize    ExaTnMpsVisitor.cpp:576-670   "norm", "exp-val-z" (shots < 1) or bit strings (shots >= 1)
 #include "B200MpsVisitor.hpp"
 
+#include <chrono>
+
 #include <algorithm>
 #include <cmath>
 
@@ -69,7 +71,20 @@ void B200MpsVisitor::check(int rc, const char* what) const {
   }
 }
 
+void B200MpsVisitor::CallStat::add(double s) {
+  if (calls == 0) { mx = s; mn = s; }
+  ++calls; total += s; mx = std::max(mx, s); mn = std::min(mn, s);
+}
+namespace {
+struct StatTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double secs() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+}  // namespace
+
 void B200MpsVisitor::initialize(std::shared_ptr<AcceleratorBuffer> in_buffer, int nbShots) {
+  StatTimer timer;
+  m_statInit = m_statFinalize = m_stat1q = m_stat2q = CallStat();
   double svdCutoff = -1.0;   // -> DBL_MIN inside the engine (ExaTnMpsVisitor.cpp:257)
   if (options.keyExists<double>("svd-cutoff")) svdCutoff = options.get<double>("svd-cutoff");
   int maxBondDim = 0;        // -> unlimited (ExaTnMpsVisitor.cpp:265)
@@ -98,6 +113,10 @@ void B200MpsVisitor::initialize(std::shared_ptr<AcceleratorBuffer> in_buffer, in
   // not a reference option: merge consecutive 2q gates on one site pair into one 4x4 (CX.Rz.CX, Swap.Swap) before the GPU
   if (options.keyExists<bool>("b200-fuse-2q") && options.get<bool>("b200-fuse-2q"))
     check(mps_set_option(m_handle, "fuse_2q", 1.0), "set_option");
+  // per-phase GPU timings (CUDA events around the merge GEMM / SVD / truncate+write-back of every layer) for getExecutionInfo()
+  if (options.keyExists<bool>("b200-profile") && options.get<bool>("b200-profile"))
+    check(mps_set_option(m_handle, "profile", 1.0), "set_option");
+  m_statInit.add(timer.secs());
 }
 
 void B200MpsVisitor::applyGate(xacc::Instruction& inst) {
@@ -106,11 +125,14 @@ void B200MpsVisitor::applyGate(xacc::Instruction& inst) {
   std::complex<double> m[16];
   const int dim = b200GateMatrix(inst.name(), params, m);
   const auto bits = inst.bits();
+  StatTimer timer;
   if (dim == 2) {
     check(mps_apply_1q(m_handle, (int)bits[0], reinterpret_cast<const double*>(m)), "apply_1q");
+    m_stat1q.add(timer.secs());
   } else {
     if (bits.size() != 2) xacc::error("two-qubit gate with " + std::to_string(bits.size()) + " bits");
     check(mps_apply_2q(m_handle, (int)bits[0], (int)bits[1], reinterpret_cast<const double*>(m)), "apply_2q");
+    m_stat2q.add(timer.secs());
   }
 }
 
@@ -126,8 +148,38 @@ void B200MpsVisitor::visit(Measure& g) {
   check(mps_measure(m_handle, (int)g.bits()[0]), "measure");
 }
 
+void B200MpsVisitor::exportStats() {
+  // Buckets the host can time (gates are queued asynchronously, so the per-call host time of a gate is its queueing cost; the
+  // GPU time of the three phases of the 2q step comes from the engine's own events when "b200-profile" is set).
+  auto put = [&](const std::string& name, const CallStat& c) {
+    executionInfo.insert(name + " [calls]", c.calls);
+    executionInfo.insert(name + " [secs]", c.total);
+    executionInfo.insert(name + " [max secs]", c.mx);
+    executionInfo.insert(name + " [min secs]", c.mn);
+  };
+  put("Initialize", m_statInit);
+  put("Finalize", m_statFinalize);
+  put("One-qubit Gate Total", m_stat1q);
+  put("Two-qubit Gate Total", m_stat2q);
+  std::vector<double> st(13, 0.0);
+  check(mps_stats(m_handle, st.data(), 13), "stats");
+  executionInfo.insert("Contract Two-Qubit Gate Tensor [secs]", st[5] * 1e-3);   // merge GEMM + gate, ExaTnMpsVisitor.cpp:1523
+  executionInfo.insert("Decompose Tensor SVD [secs]", st[6] * 1e-3);             // :1626
+  executionInfo.insert("Truncate SVD Tensor [secs]", st[7] * 1e-3);              // :1718 (fused with the write-back here)
+  executionInfo.insert("Contract Single-Qubit Gate Tensor [calls]", (int)st[1]); // 1q gates that ran as their own kernel (:1256)
+  executionInfo.insert("Two-qubit Gate Total [gpu gates]", (int)st[0]);
+  executionInfo.insert("b200-gates-2q", st[0]);
+  executionInfo.insert("b200-layers", st[2]);
+  executionInfo.insert("b200-jacobi-sweeps", st[3]);
+  executionInfo.insert("b200-kernel-launches", st[4]);
+  executionInfo.insert("b200-svd-nonconverged", st[11]);
+  executionInfo.insert("b200-norm-guard-violations", st[12]);
+  executionInfo.insert("b200-discarded-weight", discardedWeight());
+}
+
 void B200MpsVisitor::finalize() {
   if (!m_handle) xacc::error("B200MpsVisitor::finalize called before initialize");
+  StatTimer timer;
   double norm = 0.0;
   check(mps_norm(m_handle, 0, &norm), "norm");
   m_buffer->addExtraInfo("norm", norm);   // reference adds it for n < 20 only (:612); harmless beyond
@@ -173,10 +225,8 @@ void B200MpsVisitor::finalize() {
       m_buffer->addExtraInfo("amplitude-imag-vec", im);
     }
   }
-  std::vector<double> st = engineStats();
-  executionInfo.insert("b200-gates-2q", st[0]);
-  executionInfo.insert("b200-kernel-launches", st[4]);
-  executionInfo.insert("b200-discarded-weight", discardedWeight());
+  m_statFinalize.add(timer.secs());
+  exportStats();
 }
 
 const double B200MpsVisitor::getExpectationValueZ(std::shared_ptr<CompositeInstruction> function) {

@@ -72,6 +72,12 @@ private:
   void applyGate(xacc::Instruction& inst);
   void check(int rc, const char* what) const;
 
+  // the reference's per-phase statistics (FunctionCallStat, ExatnUtils.hpp:57-126; buckets named at ExaTnMpsVisitor.cpp:345,
+  // 680, 1256, 1292, 1523, 1553, 1626, 1711, 1718, 1729), exported through getExecutionInfo() instead of being printed
+  struct CallStat { double total = 0, mx = 0, mn = 0; int calls = 0; void add(double s); };
+  CallStat m_statInit, m_statFinalize, m_stat1q, m_stat2q;
+  void exportStats();
+
   mps_handle_t m_handle = nullptr;
   int m_nQubits = 0;
   int m_shotCount = -1;

@@ -179,7 +179,7 @@ int main(int argc, char** argv) {
   std::string file;
   int nq = 0, shots = -1, maxBond = 0, seed = -1, device = 0, gauge = 0;
   double cutoff = -1.0;
-  bool wantState = false, dumpNN = false, fuse2q = false;
+  bool wantState = false, dumpNN = false, fuse2q = false, profile = false;
   int repeat = 1;   // run execute() this many times on the same visitor instance (TNQVM.cpp:109 reuses it); every wall time is reported
   std::vector<double> executeMs;
   std::string bitstring, observe;
@@ -198,6 +198,7 @@ int main(int argc, char** argv) {
     else if (a == "--dump-nn") dumpNN = true;   // print the nearest-neighbourised program and exit (no GPU needed)
     else if (a == "--bitstring") bitstring = next();
     else if (a == "--fuse-2q") fuse2q = true;
+    else if (a == "--profile") profile = true;   // per-phase GPU timings in the execution info (getExecutionInfo())
     else if (a == "--repeat") repeat = std::max(1, atoi(next().c_str()));
     else if (a == "--observe") observe = next();   // VQE mode: semicolon-separated Pauli words, e.g. "X0X1;Y0Y1;Z0;Z1"
     else { fprintf(stderr, "usage: b200_tnqvm_run --xasm FILE|- [--qubits N] [--shots S] [--max-bond-dim D] [--svd-cutoff E] [--seed K] [--state] [--bitstring 01x1..] [--fuse-2q] [--observe \"X0X1;Z0\"]\n"); return 2; }
@@ -231,6 +232,7 @@ int main(int argc, char** argv) {
       opts.insert("bitstring", bits);
     }
     if (fuse2q) opts.insert("b200-fuse-2q", true);
+    if (profile) opts.insert("b200-profile", true);
     opts.insert("b200-device", device);
     opts.insert("b200-gauge", gauge);
     auto visitor = std::make_shared<tnqvm::B200MpsVisitor>();
@@ -285,6 +287,16 @@ int main(int argc, char** argv) {
       printf(", \"state\": [");
       for (size_t i = 0; i < sv.size(); ++i) printf("%s[%.17g, %.17g]", i ? ", " : "", sv[i].real(), sv[i].imag());
       printf("]");
+    }
+    {   // TNQVMVisitor::getExecutionInfo(): the reference's stat bucket names + engine counters
+      printf(", \"execution_info\": {");
+      bool firstInfo = true;
+      const HeterogeneousMap execInfo = visitor->getExecutionInfo();   // returned by value
+      for (auto& kv : execInfo.raw()) {
+        if (auto d = std::any_cast<double>(&kv.second)) { printf("%s\"%s\": %.9g", firstInfo ? "" : ", ", kv.first.c_str(), *d); firstInfo = false; }
+        else if (auto i = std::any_cast<int>(&kv.second)) { printf("%s\"%s\": %d", firstInfo ? "" : ", ", kv.first.c_str(), *i); firstInfo = false; }
+      }
+      printf("}");
     }
     auto st = visitor->engineStats();
     printf(", \"stats\": {\"gates_2q\": %.0f, \"layers\": %.0f, \"jacobi_sweeps\": %.0f, \"launches\": %.0f}}\n", st[0], st[2], st[3], st[4]);

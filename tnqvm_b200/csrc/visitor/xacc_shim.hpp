@@ -46,6 +46,7 @@ public:
   bool stringExists(const std::string& k) const { return keyExists<std::string>(k); }
   std::string getString(const std::string& k) const { return get<std::string>(k); }
   void merge(const HeterogeneousMap& o) { for (auto& kv : o.items) items[kv.first] = kv.second; }
+  const std::map<std::string, std::any>& raw() const { return items; }   // shim only: lets the driver print what a visitor exported
 private:
   std::map<std::string, std::any> items;
 };
