@@ -135,7 +135,7 @@ struct Oracle {
   int use_gesdd = 0;
   int gauge = 0;                 // 0 reference (U sqrtS | sqrtS Vh); 1 (U | S Vh); 2 (U S | Vh)
   int renorm = 0;                // never in the reference
-  double null_tol = 0;           // > 0: singular values <= null_tol * sigma_max are rounding noise of an exact zero and are set to 0.0 before the
+  double null_tol = 0;           // > 0: singular values <= null_tol * ||theta||_F are rounding noise of an exact zero and are set to 0.0 before the
                                  // reference's cut rule runs (NOT in the reference: it mirrors the engine's documented deviation)
   std::vector<std::vector<double>> sv;   // last retained singular values per bond
   double discarded = 0;          // accumulated discarded weight (not in reference; diagnostic)
@@ -245,8 +245,12 @@ extern "C" int oracle_apply_2q(Oracle* o, int q0, int q1, const double* m_ri) {
   if (info != 0) return 3;
   double t2 = now_s();
   o->t_svd += t2 - t1;
-  if (o->null_tol > 0)
-    for (int k = 1; k < r; ++k) if (S[k] <= o->null_tol * S[0]) S[k] = 0.0;
+  if (o->null_tol > 0) {
+    double fro = 0;
+    for (int k = 0; k < r; ++k) fro += S[k] * S[k];
+    fro = std::sqrt(fro);
+    for (int k = 1; k < r; ++k) if (S[k] <= o->null_tol * fro) S[k] = 0.0;
+  }
   // truncateSvdTensors (:2366-2536).  Under the reference gauge both partial norms equal
   // sigma_k (sum of squares, comment :2421-2423) or sqrt(sigma_k) (true 2-norm).
   int cut = r;

@@ -697,8 +697,9 @@ def test_site_sharded_handle_matches_single_engine(O, devices, partition_by):
     assert (a.bond_dims() == b.bond_dims()).all()
     assert np.abs(a.expval_z_all() - b.expval_z_all()).max() < 1e-12
     assert abs(a.norm() - b.norm()) < 1e-12
-    pairs = [(0, 1), (lay[1] - 1, lay[1]), (3, n - 1)]
-    assert np.abs(a.expval_zz_pairs(pairs) - b.expval_zz_pairs(pairs)).max() < 1e-12
+    pairs = [(0, 1), (lay[1] - 1, lay[1]), (3, n - 1), (lay[1], lay[1]), (lay[1] - 2, lay[1] + 1), (n - 2, n - 1)]
+    assert np.abs(a.expval_zz_pairs(pairs) - b.expval_zz_pairs(pairs)).max() < 1e-12   # environments hop across the block boundaries
+    assert abs(a.expval_z([1, lay[1], n - 1]) - b.expval_z([1, lay[1], n - 1])) < 1e-12
     bits = [k % 2 for k in range(n)]
     assert abs(a.amplitude(bits) - b.amplitude(bits)) < 1e-12
     for k in (0, lay[1] - 1, lay[1], n - 2):

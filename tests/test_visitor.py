@@ -167,3 +167,17 @@ def test_visitor_execution_info_has_the_reference_stat_buckets():
         assert info[key] > 0.0, key
     assert info["Two-qubit Gate Total [gpu gates]"] == n2 and info["b200-kernel-launches"] > 0
     assert info["b200-svd-nonconverged"] == 0
+
+
+@pytest.mark.gpu
+def test_visitor_site_sharded_option_matches_single_device():
+    """{"b200-devices", [..]} through the C++ visitor: the sharded run (two site blocks; both on GPU 0 when the box has one GPU)
+    gives the buffer outputs of the single-device run."""
+    import torch
+    n = 14
+    circ = Cc.brickwork(n, 7, seed=4, prefix_ghz=True) + [("Measure", (q,), ()) for q in (0, 5, 13)]
+    devs = "0,1" if torch.cuda.device_count() > 1 else "0,0"
+    a = json.loads(run(circ, n, "--max-bond-dim", 16).strip().splitlines()[-1])
+    b = json.loads(run(circ, n, "--max-bond-dim", 16, "--devices", devs).strip().splitlines()[-1])
+    assert abs(a["norm"] - b["norm"]) < 1e-12 and abs(a["exp-val-z"] - b["exp-val-z"]) < 1e-12
+    assert a["bond_dims"] == b["bond_dims"]

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(CT, 4) jacobi_cluster_sweep_kernel(const Jacob
       }
       if (tid == 0) s_flag = 0;
       __syncthreads();
-      const double dead_abs = dead2 * fro2[mat] / (double)N;
+      const double dead_abs = dead2 * fro2[mat];   // (null_tol * ||G||_F)^2: above the rounding-noise floor eps * sigma_max * sqrt(rotations) of a null column
       const double2* wdA = P.wd + (size_t)blkA * 64;
       const double2* wdB = P.wd + (size_t)(blkB >= 0 ? blkB : blkA) * 64;
       for (int i = tid; i < 256; i += CT) {

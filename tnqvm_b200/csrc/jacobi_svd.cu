@@ -71,9 +71,12 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
                                           const double* __restrict__ fro2, int* __restrict__ dirty) {
   const int M = P.M, N = P.N, ldg = P.ldg;
   double2* G = P.G;
-  // columns whose squared norm is below dead_abs (<= (null_tol * sigma_max)^2) are numerically null: they are zeroed at
-  // write-back and never rotated, so rank-deficient thetas do not spend sweeps orthogonalising rounding noise
-  const double dead_abs = dead2 * fro2[mat] / (double)N;
+  // columns whose squared norm is below dead_abs = (null_tol * ||G||_F)^2 are numerically null: they are zeroed at write-back
+  // (trunc_kernel applies the same threshold to the singular values) and never rotated, so rank-deficient thetas do not spend
+  // sweeps orthogonalising rounding noise.  The threshold is relative to the Frobenius norm, not to ||G||_F / sqrt(N): the
+  // null columns of a rank-deficient 1024-column theta sit at ~1e-13 ||G||_F after a few sweeps (eps x sigma_max x the rotations
+  // that touched them), and with the lower threshold they kept rotating against each other for ever (profiles/r04n_*)
+  const double dead_abs = dead2 * fro2[mat];   // (null_tol * ||G||_F)^2: above the rounding-noise floor eps * sigma_max * sqrt(rotations) of a null column
 
   __shared__ int s_cols[16];
   constexpr int NT = 32 * NWARP;
@@ -518,15 +521,19 @@ __global__ void __launch_bounds__(256) trunc_kernel(const TruncProblem* __restri
   __syncthreads();
   __shared__ int s_keep;
   __shared__ double s_rn;
-  // numerically-null singular values stand for exact zeros (engine.cu, null_tol): report them as 0.0 so that the reference's cut
-  // rule below sees what an exact SVD would have returned
-  {
-    const double s0 = P.sigma[0];
-    __syncthreads();
-    for (int k = tid; k < N; k += 256)
-      if (k > 0 && P.sigma[k] <= null_tol * s0) P.sigma[k] = 0.0;
-    __syncthreads();
+  // numerically-null singular values (sigma_k <= null_tol * ||theta||_F, the threshold below which the sweeps leave a column
+  // alone) stand for exact zeros: report them as 0.0 so that the reference's cut rule below sees what an exact SVD would
+  // have returned
+  __shared__ double s_fro;
+  if (tid == 0) {
+    double t = 0.0;
+    for (int k = 0; k < N; ++k) t += P.sigma[k] * P.sigma[k];
+    s_fro = sqrt(t);
   }
+  __syncthreads();
+  for (int k = tid; k < N; k += 256)
+    if (k > 0 && P.sigma[k] <= null_tol * s_fro) P.sigma[k] = 0.0;
+  __syncthreads();
   if (tid == 0) {
     // truncateSvdTensors, ExaTnMpsVisitor.cpp:2434-2445: first k whose partial norm is below eps, PLUS ONE
     int cut = N;
@@ -555,7 +562,7 @@ __global__ void __launch_bounds__(256) trunc_kernel(const TruncProblem* __restri
     double sP = 0.0, sO = 0.0;
     // sigma_k <= null_tol * sigma_max is numerically null: without an accumulated V its right vector is noise amplified by
     // tol * sigma_max / sigma_k, so both factors of that component are dropped (contribution to theta <= null_tol * sigma_max)
-    if (s > 1e-100 && s > null_tol * P.sigma[0]) {
+    if (s > 1e-100 && s > null_tol * s_fro) {
       // lo site carries sigma^el, hi site sigma^eh
       const double lo_f = (gauge == 0) ? sqrt(s) : (gauge == 1 ? 1.0 : s);
       const double hi_f = ((gauge == 0) ? sqrt(s) : (gauge == 1 ? s : 1.0)) * s_rn;

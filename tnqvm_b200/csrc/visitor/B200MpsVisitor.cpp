@@ -103,7 +103,14 @@ void B200MpsVisitor::initialize(std::shared_ptr<AcceleratorBuffer> in_buffer, in
   // the registered service instance is reused across execute() calls (TNQVM.cpp:109): a fresh state every time
   if (m_handle) { mps_destroy(m_handle); m_handle = nullptr; }
   m_nQubits = n;
-  const int rc = mps_create(n, 1, maxBondDim, svdCutoff, gauge, device, seed, &m_handle);
+  // {"b200-devices", vector<int>}: shard the sites over these GPUs of the box (what the MPI build of the reference does with one
+  // rank per site block, ExaTnMpsVisitor.cpp:347-531); {"b200-partition-by-count", true} = equal site counts instead of equal cost
+  std::vector<int> devices;
+  if (options.keyExists<std::vector<int>>("b200-devices")) devices = options.get<std::vector<int>>("b200-devices");
+  const bool byCount = options.keyExists<bool>("b200-partition-by-count") && options.get<bool>("b200-partition-by-count");
+  const int rc = devices.size() > 1
+                     ? mps_create_sharded(n, maxBondDim, svdCutoff, gauge, (int)devices.size(), devices.data(), byCount ? 0 : 1, seed, &m_handle)
+                     : mps_create(n, 1, maxBondDim, svdCutoff, gauge, devices.size() == 1 ? devices[0] : device, seed, &m_handle);
   if (rc != 0) {
     const char* msg = mps_last_error(nullptr);
     xacc::error(std::string("B200MpsVisitor: cannot create the MPS engine: ") + (msg ? msg : "?"));

@@ -182,7 +182,7 @@ int main(int argc, char** argv) {
   bool wantState = false, dumpNN = false, fuse2q = false, profile = false;
   int repeat = 1;   // run execute() this many times on the same visitor instance (TNQVM.cpp:109 reuses it); every wall time is reported
   std::vector<double> executeMs;
-  std::string bitstring, observe;
+  std::string bitstring, observe, devices;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     auto next = [&]() { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return std::string(argv[++i]); };
@@ -198,6 +198,7 @@ int main(int argc, char** argv) {
     else if (a == "--dump-nn") dumpNN = true;   // print the nearest-neighbourised program and exit (no GPU needed)
     else if (a == "--bitstring") bitstring = next();
     else if (a == "--fuse-2q") fuse2q = true;
+    else if (a == "--devices") devices = next();   // comma-separated GPU indices: site-sharded run
     else if (a == "--profile") profile = true;   // per-phase GPU timings in the execution info (getExecutionInfo())
     else if (a == "--repeat") repeat = std::max(1, atoi(next().c_str()));
     else if (a == "--observe") observe = next();   // VQE mode: semicolon-separated Pauli words, e.g. "X0X1;Y0Y1;Z0;Z1"
@@ -233,6 +234,12 @@ int main(int argc, char** argv) {
     }
     if (fuse2q) opts.insert("b200-fuse-2q", true);
     if (profile) opts.insert("b200-profile", true);
+    if (!devices.empty()) {
+      std::vector<int> dv;
+      std::stringstream ds(devices);
+      for (std::string t; std::getline(ds, t, ',');) if (!t.empty()) dv.push_back(atoi(t.c_str()));
+      opts.insert("b200-devices", dv);
+    }
     opts.insert("b200-device", device);
     opts.insert("b200-gauge", gauge);
     auto visitor = std::make_shared<tnqvm::B200MpsVisitor>();
