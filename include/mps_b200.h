@@ -68,7 +68,7 @@ int mps_restore(mps_handle_t h);
  * "layer_batch" (0 = execute gate by gate), "norm_guard" (post-SVD check of ExaTnMpsVisitor.cpp:1632-1661: 2 = the reference's
  * Release-build behaviour (default): report once on stderr, count in mps_stats[12]; 1 = its Debug-build behaviour: the call fails;
  * 0 = off), "null_tol" (components with sigma <= null_tol * ||theta||_F are treated as the exact zeros they
- * stand for and dropped; <= 0 (default): 10 x the Jacobi tolerance.  A documented deviation: LAPACK inside ExaTN keeps them as noise).  Options that change how queued gates execute flush the queue first.
+ * stand for and dropped; <= 0 (default): 1e-13, independent of the matrix size and of what is batched together.  A documented deviation: LAPACK inside ExaTN keeps them as noise).  Options that change how queued gates execute flush the queue first.
  * Engine variants kept for A/B measurements, all parity-tested (tests/test_gpu_parity.py): "qr_prereduce" (default 1),
  * "jacobi_ctas_per_sm" (0 = by load, 1..4), "jacobi_wide_tasks" (1: eight warps per pair task when at most two tasks per SM
  * are resident), "jacobi_chunk_mb" (Jacobi work matrices of a layer run in chunks of at most this many MiB so that a chunk

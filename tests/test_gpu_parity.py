@@ -168,7 +168,7 @@ def test_truncated_parity_within_reference_spread(O, n, depth, chi):
     # factors, :1623) a noise singular value ~1e-17 leaves ~1e-9 on each neighbour, which the next SVD on an adjacent bond
     # reports as a "singular value" of that size.  The engine treats numerically-null components as the zeros they stand for
     # (`null_tol`); the oracle mirrors the rule, and then bond dimensions agree as well.
-    o = O.OracleMPS(n, max_bond=chi, null_tol=10.0 * math.sqrt(2.0 * chi) * 2.220446049250313e-16).run(circ)
+    o = O.OracleMPS(n, max_bond=chi, null_tol=engine_null_tol()).run(circ)
     zo = np.array([o.expval_z([k]) for k in range(n)])
     assert np.abs(e.expval_z_all() - zo).max() < TRUNC_TOL
     assert abs(e.norm() - o.norm()) < TRUNC_TOL
@@ -475,9 +475,9 @@ def test_snapshot_restore_returns_the_exact_state(O):
 EPS = 2.220446049250313e-16
 
 
-def engine_null_tol(chi):
-    """the engine's automatic numerically-null threshold for thetas of 2 chi rows: 10 x sqrt(rows) x eps"""
-    return 10.0 * math.sqrt(2.0 * chi) * EPS
+def engine_null_tol(chi=None):
+    """the engine's numerically-null threshold (relative to ||theta||_F): a constant, see engine.cu"""
+    return 1e-13
 
 
 def dependency_layers(n, circ):

@@ -151,7 +151,7 @@ struct mps_b200_handle {
   std::vector<int> last_touch;   // per site: index in `queue` of the last queued gate on it (-1: none since the flush)
   double nfused2q = 0;
   double jacobi_tol = 0.0;   // 0 -> sqrt(M) * eps
-  // Numerically-null components: sigma_k <= null_tol * ||theta||_F (<= 0: automatic, 10 x the Jacobi tolerance) is rounding noise
+  // Numerically-null components: sigma_k <= null_tol * ||theta||_F (<= 0: the default 1e-13) is rounding noise
   // of an exact zero.  Such columns are not rotated by the Jacobi sweeps and both factors of the component are zeroed at
   // write-back.  This is a DOCUMENTED DEVIATION from the reference, where LAPACK inside ExaTN returns noise singular values
   // (~1e-17 sigma_max) with arbitrary orthonormal vectors for rank-deficient thetas and the cut rule of :2434-2443 only drops
@@ -646,9 +646,16 @@ struct mps_b200_handle {
 
     // ---- Jacobi sweeps
     const double eps = 2.220446049250313e-16;
-    const double tol = jacobi_tol > 0 ? jacobi_tol : std::sqrt((double)maxMg) * eps;
+    // relative rotation tolerance: sqrt(rows) eps, but never below sqrt(2048) eps = 1e-14 so that, up to chi = 1024, it does not
+    // depend on which matrices share a layer (one GPU vs a sharded chain, layer_batch on / off give the same rotations)
+    const double tol = jacobi_tol > 0 ? jacobi_tol : std::max(std::sqrt((double)maxMg), std::sqrt(2048.0)) * eps;
     const double tol2_base = tol * tol;
-    const double ntol = null_tol > 0 ? null_tol : 10.0 * tol;   // numerically-null threshold relative to sigma_max
+    // numerically-null threshold relative to ||theta||_F.  A CONSTANT (1e-13 ~ 10 sqrt(2048) eps), not a function of the layer:
+    // a threshold that followed the largest matrix of the layer made the null decisions of a small chain-end gate depend on
+    // what else happened to be batched with it -- and in the sqrt(S) gauge a borderline component that is kept instead of
+    // dropped is amplified at the following gates, so the same circuit gave different truncated states on one
+    // GPU and sharded over eight (bench.py circuit_sharded parity 0.24 in the norm, profiles/r04p_*)
+    const double ntol = null_tol > 0 ? null_tol : 1e-13;
     const double dead2_base = ntol * ntol;
     const size_t remBytes = (sizeof(int) * 2 * (size_t)(max_sweeps + 4) * chunks.size() + 255) & ~size_t(255);
     int* h_rem = (int*)pinned_rb(remBytes + sizeof(int) * (B + 4) + sizeof(double) * (2 * B + sig_total) + 256);
@@ -1558,6 +1565,13 @@ void group_build_envs(mps_b200_handle* h, GroupEnvs& G, bool keep_fh, int nscal)
     D.scal = (double2*)(b + oS); D.dots = (DotProblem*)(b + oP); D.part = (double2*)(b + oPart);
   }
   const cplx one(1, 0);
+  // the second streams read the sites the main streams may still be writing (write-back of the last gates): fork first
+  for (int d = 0; d < P; ++d) {
+    mps_b200_handle* S = grp.sub[d];
+    CK(cudaSetDevice(S->device));
+    CK(cudaEventRecord(S->fork_ev, S->stream));
+    CK(cudaStreamWaitEvent(S->stream2, S->fork_ev, 0));
+  }
   // left-to-right chain (main streams)
   for (int d = 0; d < P; ++d) {
     mps_b200_handle* S = grp.sub[d];

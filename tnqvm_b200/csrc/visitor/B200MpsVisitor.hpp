@@ -79,6 +79,10 @@ private:
   void exportStats();
 
   mps_handle_t m_handle = nullptr;
+  std::vector<int> m_devices;   // placement the handle was created with (the handle is reused across execute() calls when unchanged)
+  bool m_byCount = false;
+  int m_maxBondAtCreate = 0;
+  std::vector<double> m_statsAtInit;   // engine counters when this execute() began (the handle outlives it)
   int m_nQubits = 0;
   int m_shotCount = -1;
   std::vector<size_t> m_measureQubits;
