@@ -4,7 +4,7 @@
 TAG=${1:-r01}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-BARGS="--prep random --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-peak"
+BARGS="--prep random --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-peak --no-extras"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv \
   python bench.py $BARGS > $OUT/ncu_bench.log 2>&1
 python scripts/summarize_launches.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1; cat $OUT/launches_summary.txt
