@@ -51,6 +51,8 @@ int mps_create(int n_qubits, int n_registers, int max_bond, double svd_cutoff, i
  * may be listed more than once (its blocks then share that GPU: how the single-GPU tests exercise the exchange logic). */
 int mps_create_sharded(int n_qubits, int max_bond, double svd_cutoff, int gauge, int n_devices, const int* devices,
                        int partition_by_cost, uint64_t seed, mps_handle_t* out);
+/* the partition formula alone (no device needed): first_site[d] for d = 0..n_devices, first_site[n_devices] = n_qubits */
+int mps_shard_partition(int n_qubits, int n_devices, int max_bond, int partition_by_cost, int* first_site);
 /* device blocks of a handle: *n_devices, and first_site[d] for d = 0..n_devices (first_site[n_devices] = n_qubits; may be NULL) */
 int mps_shard_layout(mps_handle_t h, int* n_devices, int* first_site);
 int mps_destroy(mps_handle_t h);

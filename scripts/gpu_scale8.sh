@@ -1,6 +1,6 @@
 #!/bin/bash
 # 8-GPU scaling evidence (run with gpurun --gpus 8)
-OUT=gpurun_out/r04p; mkdir -p $OUT
+TAG=${1:-scale8}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 nvidia-smi -L > $OUT/gpu.txt
 timeout 300 python -m pytest tests -m gpu -q -k "sharded or nccl" > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest.log
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 scripts/config4_sweep.py > $OUT/config4.json 2> $OUT/config4.err; grep config $OUT/config4.json | cut -c1-600; tail -2 $OUT/config4.err

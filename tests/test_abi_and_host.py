@@ -127,3 +127,28 @@ def test_plugin_activator_registers_the_visitor_service():
         with tempfile.TemporaryDirectory() as tmp:
             c = subprocess.run(["cmake", "-S", os.path.join(plug, "cmake_check"), "-B", tmp, "-DMPS_B200_ROOT=" + ROOT], capture_output=True, text=True, timeout=300)
             assert c.returncode == 0, c.stdout[-1500:] + c.stderr[-1500:]
+
+
+def test_shard_partition_formula_matches_the_host_restatement():
+    """mps_shard_partition (the site-block formula of mps_create_sharded, callable without a device) against
+    tnqvm_b200.sharded.partition: equal counts and equal estimated SVD cost; contiguous, non-empty blocks covering all sites."""
+    from tnqvm_b200 import abi
+    L = abi.load_library()
+    try:
+        from tnqvm_b200.sharded import partition
+    except Exception:
+        partition = None
+    for n in (2, 5, 16, 50, 53, 100):
+        for world in (1, 2, 3, 4, 8):
+            if world > n:
+                continue
+            for chi, by_cost in ((0, 0), (64, 1), (256, 1), (1024, 1)):
+                out = (ctypes.c_int * (world + 1))()
+                assert L.mps_shard_partition(n, world, chi, by_cost, out) == 0
+                first = list(out)
+                assert first[0] == 0 and first[-1] == n and all(a < b for a, b in zip(first, first[1:])), (n, world, chi, first)
+                if partition is not None:
+                    ref = partition(n, world, chi if by_cost else 0)
+                    assert first == [s for s, _ in ref] + [n], (n, world, chi, first, ref)
+    out = (ctypes.c_int * 4)()
+    assert L.mps_shard_partition(2, 3, 0, 0, out) != 0   # fewer sites than devices

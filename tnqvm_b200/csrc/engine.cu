@@ -1940,6 +1940,18 @@ int mps_create_sharded(int n_qubits, int max_bond, double svd_cutoff, int gauge,
   }
 }
 
+int mps_shard_partition(int n_qubits, int n_devices, int max_bond, int partition_by_cost, int* first_site) {
+  try {
+    const auto b = shard_partition(n_qubits, n_devices, max_bond, partition_by_cost != 0);
+    for (int d = 0; d < n_devices; ++d) first_site[d] = b[d].first;
+    first_site[n_devices] = n_qubits;
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return 2;
+  }
+}
+
 int mps_shard_layout(mps_handle_t h, int* n_devices, int* first_site /* n_devices + 1 entries, may be NULL */) {
   API_BEGIN(h)
   const int P = h->grp ? (int)h->grp->sub.size() : 1;
