@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(PT, 1) qr_panel_kernel(const QrProblem* __rest
         a[i] = b0;
         if (next && i > j + 1) n0 += b0.x * b0.x + b0.y * b0.y;
       }
+      __syncwarp();   // every lane has read a[j] (aj) before lane 0 replaces it
       if (lane == 0) a[j] = make_double2(aj.x - f.x, aj.y - f.y);
       if (next) { n0 = warp_sum(n0 + n1); if (lane == 0) s_nrm[j + 1] = n0; }
     } else if (warp == j + 1 && warp < pw && !live) {
