@@ -152,3 +152,20 @@ def test_shard_partition_formula_matches_the_host_restatement():
                     assert first == [s for s, _ in ref] + [n], (n, world, chi, first, ref)
     out = (ctypes.c_int * 4)()
     assert L.mps_shard_partition(2, 3, 0, 0, out) != 0   # fewer sites than devices
+
+
+def test_python_gate_table_equals_the_reference_table_and_knows_s_sdg_u3():
+    """tnqvm_b200.gates.gate_matrix (the Python host path) against the oracle's table, which is pinned bit for bit to the
+    reference's Gates.hpp (tests/test_oracle_golden.py); S, Sdg and the U3 alias -- gates the reference header names but gives no
+    matrix for, and which the C++ B200MpsVisitor applies natively -- have their textbook matrices on both host surfaces."""
+    import cmath
+    from oracle import oracle as O   # checker only
+    from tnqvm_b200.gates import gate_matrix
+    for nm, pr in [("H", ()), ("X", ()), ("Y", ()), ("Z", ()), ("T", ()), ("Tdg", ()), ("Rx", (0.3,)), ("Ry", (0.7,)), ("Rz", (-1.1,)),
+                   ("U", (0.3, 0.4, 0.5)), ("CNOT", ()), ("CZ", ()), ("CY", ()), ("CH", ()), ("CRZ", (0.9,)), ("CPhase", (0.2,)),
+                   ("Swap", ()), ("iSwap", ()), ("fSim", (0.4, 0.6)), ("I", ())]:
+        assert np.array_equal(np.asarray(gate_matrix(nm, pr)), np.asarray(O.gate_matrix(nm, pr))), nm
+    assert np.allclose(gate_matrix("S", ()), [[1, 0], [0, 1j]]) and np.allclose(gate_matrix("Sdg", ()), [[1, 0], [0, -1j]])
+    assert np.array_equal(np.asarray(gate_matrix("U3", (0.3, 0.4, 0.5))), np.asarray(gate_matrix("U", (0.3, 0.4, 0.5))))
+    assert np.allclose(np.asarray(gate_matrix("S", ())) @ np.asarray(gate_matrix("S", ())), np.asarray(gate_matrix("Z", ())))
+    assert abs(np.asarray(gate_matrix("T", ()))[1, 1] - cmath.exp(0.25j * cmath.pi)) < 1e-16
