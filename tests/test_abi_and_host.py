@@ -1,6 +1,7 @@
 """CPU-side checks: the C-ABI library loads and exports every symbol include/mps_b200.h declares (no compute
 without a GPU), the product refuses to run without CUDA (no fallback), and the host-side circuit logic."""
 import ctypes
+import math
 import os
 import re
 
@@ -169,3 +170,39 @@ def test_python_gate_table_equals_the_reference_table_and_knows_s_sdg_u3():
     assert np.array_equal(np.asarray(gate_matrix("U3", (0.3, 0.4, 0.5))), np.asarray(gate_matrix("U", (0.3, 0.4, 0.5))))
     assert np.allclose(np.asarray(gate_matrix("S", ())) @ np.asarray(gate_matrix("S", ())), np.asarray(gate_matrix("Z", ())))
     assert abs(np.asarray(gate_matrix("T", ()))[1, 1] - cmath.exp(0.25j * cmath.pi)) < 1e-16
+
+
+def test_xasm_parameters_are_parsed_not_evaluated():
+    """load_xasm must not eval() gate parameters (a .xasm file is untrusted input).  Arithmetic with pi works,
+    anything else is rejected."""
+    n, circ = Cc.load_xasm("Rx(q[0], pi/2);\nRz(q[1], -0.25*pi + 1e-3);\nfSim(q[0], q[3], (1.5707963267948966), 2**-1);\nCX(q[1], q[2]);\n")
+    assert n == 4 and circ[0][0] == "Rx" and abs(circ[0][2][0] - math.pi / 2) < 1e-15
+    assert abs(circ[1][2][0] - (-0.25 * math.pi + 1e-3)) < 1e-15 and circ[2][2] == (1.5707963267948966, 0.5) and circ[3][0] == "CNOT"
+    for bad in ("Rx(q[0], __import__('os').system('true'));",
+                "Rx(q[0], ().__class__.__base__.__subclasses__());",
+                "Rx(q[0], open('/etc/passwd'));",
+                "Rx(q[0], pi if 1 else 2);",
+                "Rx(q[0], [1][0]);",
+                "Rx(q[0], 'a');"):
+        with pytest.raises(ValueError):
+            Cc.load_xasm(bad)
+
+
+def test_real_sycamore_fixture_is_the_reference_circuit():
+    """tests/golden/circuits/sycamore_53_14_0.json.gz (written by tests/golden/make_sycamore_fixture.py from the reference's
+    examples/sycamore/resources/sycamore_53_14_0.xasm): 53 qubits, 2527 1q + 301 fSim gates, coupler distances 1..10, and
+    1897 nearest-neighbour 2q gates after the routing pass.  In the build container the fixture is also
+    compared gate for gate with the resource file itself."""
+    n, circ = Cc.sycamore_53(14)
+    assert n == 53 and Cc.count_gates(circ) == (2527, 301)
+    assert {g[0] for g in circ} == {"Rx", "Ry", "Rz", "fSim"}
+    dist = {abs(g[1][0] - g[1][1]) for g in circ if len(g[1]) == 2}
+    assert min(dist) == 1 and max(dist) == 10
+    nn = Cc.nearest_neighbor(circ)
+    assert Cc.count_gates(nn) == (2527, 1897) and all(abs(g[1][0] - g[1][1]) == 1 for g in nn if len(g[1]) == 2)
+    src = "/root/reference/examples/sycamore/resources/sycamore_53_14_0.xasm"
+    if os.path.exists(src):
+        n2, ref = Cc.load_xasm(open(src).read())
+        assert n2 == n and len(ref) == len(circ)
+        for a, b in zip(ref, circ):
+            assert a[0] == b[0] and tuple(a[1]) == tuple(b[1]) and np.allclose(a[2], b[2], rtol=0, atol=0)
