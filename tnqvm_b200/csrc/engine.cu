@@ -732,6 +732,11 @@ struct mps_b200_handle {
           if (per_sm <= 0) per_sm = (int)std::max<long>(1, std::min<long>(4, (want + sm_count - 1) / sm_count));
           // at most two tasks per SM: give each task eight warps (the register file holds 2 x 256 threads of this kernel)
           if (wide_tasks && per_sm <= 2) warps = 8;
+          // at most one task per SM (a lone gate per layer in routed circuits, the straggler tail of a layer): sixteen warps --
+          // the update phase is then one or two rows per thread instead of four, and that phase is a per-thread latency chain
+          // (load 16 values, 64 dependent plane rotations, store): 14.7 of the 22.8 us a tournament step of a lone
+          // 1024-row matrix takes (profiles/r04z_*)
+          if (wide_tasks && ctas_per_sm <= 0 && est <= sm_count) { warps = 16; per_sm = 1; }
           launch_jacobi_sweep(dJ + c0, rotating, cpairs, csteps, queued * csteps, tol2, dead2, d_fro2 + c0, d_dirty + c0, d_done + c0,
                               d_prog + (size_t)c0 * pstride, pstride, d_ccnt + queued, d_crem + 1, sm_count * per_sm, warps, d_active, stream);
           launch_jacobi_check(CB, d_dirty + c0, d_done + c0, d_crem, d_active, stream);

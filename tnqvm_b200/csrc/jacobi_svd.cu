@@ -55,7 +55,7 @@ __device__ __forceinline__ bool pair_blocks(const JacobiProblem& P, int step, in
 // one pair task: Gram (phase A), rotations (phase B), apply (phase C) on the 16 columns of blocks (blkA, blkB).
 // All exits are uniform over the CTA.  Loads of G bypass L1 (ld.global.cg): inside the persistent sweep kernel the
 // columns were last written by a CTA on another SM.
-// NWARP = warps per task: 4 when the SMs hold several tasks each, 8 when a tournament step has fewer tasks than SMs (layers
+// NWARP = warps per task: 4 when the SMs hold several tasks each, 8 (16) when a tournament step has at most two (one) tasks per SM (layers
 // of one to four gates in routed circuits) and the latency of the two streaming phases of a lone task is what counts.
 //
 // Phase C applies the rotations of phase B to the rows of X directly (one thread per row, the 16 entries of the row in
@@ -80,7 +80,8 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
 
   __shared__ int s_cols[16];
   constexpr int NT = 32 * NWARP;
-  __shared__ double s_red[NWARP][7][64];
+  constexpr int NRED = NWARP < 8 ? NWARP : 8;   // partial-sum slots: sixteen-warp tasks fold warps 8-15 onto 0-7 (static shared memory stays < 48 KB)
+  __shared__ double s_red[NRED][7][64];
   __shared__ double2 sW[16 * WLD];
   __shared__ double2 s_tp[MAXROT], s_tq[MAXROT];   // scaled rotation parameters in application order
   __shared__ double s_gam[16], s_igam[16];
@@ -172,13 +173,28 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     }
     // C fragment: element (row = lane>>2, col = 2*(lane&3)+e)
     const int e0 = (lane >> 2) * 8 + 2 * (lane & 3);
-    s_red[warp][0][e0] = w00[0]; s_red[warp][0][e0 + 1] = w00[1];
-    s_red[warp][1][e0] = m00[0]; s_red[warp][1][e0 + 1] = m00[1];
-    s_red[warp][2][e0] = w11[0]; s_red[warp][2][e0 + 1] = w11[1];
-    s_red[warp][3][e0] = m11[0]; s_red[warp][3][e0 + 1] = m11[1];
-    s_red[warp][4][e0] = w01[0]; s_red[warp][4][e0 + 1] = w01[1];
-    s_red[warp][5][e0] = p01[0]; s_red[warp][5][e0 + 1] = p01[1];
-    s_red[warp][6][e0] = q01[0]; s_red[warp][6][e0 + 1] = q01[1];
+    if (warp < NRED) {
+      s_red[warp][0][e0] = w00[0]; s_red[warp][0][e0 + 1] = w00[1];
+      s_red[warp][1][e0] = m00[0]; s_red[warp][1][e0 + 1] = m00[1];
+      s_red[warp][2][e0] = w11[0]; s_red[warp][2][e0 + 1] = w11[1];
+      s_red[warp][3][e0] = m11[0]; s_red[warp][3][e0 + 1] = m11[1];
+      s_red[warp][4][e0] = w01[0]; s_red[warp][4][e0 + 1] = w01[1];
+      s_red[warp][5][e0] = p01[0]; s_red[warp][5][e0 + 1] = p01[1];
+      s_red[warp][6][e0] = q01[0]; s_red[warp][6][e0 + 1] = q01[1];
+    }
+    if (NWARP > NRED) {   // second half of the warps adds onto the first half's slots (fixed order: deterministic)
+      __syncthreads();
+      if (warp >= NRED) {
+        const int w2 = warp - NRED;
+        s_red[w2][0][e0] += w00[0]; s_red[w2][0][e0 + 1] += w00[1];
+        s_red[w2][1][e0] += m00[0]; s_red[w2][1][e0 + 1] += m00[1];
+        s_red[w2][2][e0] += w11[0]; s_red[w2][2][e0 + 1] += w11[1];
+        s_red[w2][3][e0] += m11[0]; s_red[w2][3][e0 + 1] += m11[1];
+        s_red[w2][4][e0] += w01[0]; s_red[w2][4][e0 + 1] += w01[1];
+        s_red[w2][5][e0] += p01[0]; s_red[w2][5][e0 + 1] += p01[1];
+        s_red[w2][6][e0] += q01[0]; s_red[w2][6][e0 + 1] += q01[1];
+      }
+    }
   }
   __syncthreads();
   if (timing) tB = clock64();
@@ -186,7 +202,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
     const int t = i >> 6, e = i & 63;
     double acc = s_red[0][t][e];
 #pragma unroll
-    for (int w = 1; w < NWARP; ++w) acc += s_red[w][t][e];
+    for (int w = 1; w < NRED; ++w) acc += s_red[w][t][e];
     s_red[0][t][e] = acc;
   }
   __syncthreads();
@@ -389,7 +405,7 @@ __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.rel
 // finished or running on resident CTAs, so the scheme cannot deadlock.  Compared with one launch per step this removes
 // ~60 launch boundaries per sweep and lets the Gram / rotate / apply phases of different pairs overlap on an SM.
 template <int NWARP>
-__global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) jacobi_sweep_kernel(const JacobiProblem* __restrict__ probs, int batch, int max_pairs, int nsteps,
+__global__ void __launch_bounds__(32 * NWARP, NWARP >= 16 ? 1 : 16 / NWARP) jacobi_sweep_kernel(const JacobiProblem* __restrict__ probs, int batch, int max_pairs, int nsteps,
                                                              int base, double tol2, double dead2, const double* __restrict__ fro2,
                                                              int* __restrict__ dirty, const int* __restrict__ done,
                                                              int* __restrict__ progress, int progress_stride, int* __restrict__ counter,
@@ -594,7 +610,10 @@ void launch_jacobi_sweep(const JacobiProblem* d_probs, int batch, int max_pairs,
   if (batch <= 0) return;
   const long total = (long)nsteps * batch * max_pairs;   // batch = upper bound of the matrices still rotating (d_active[0] on the device)
   const int grid = (int)std::min<long>(total, grid_ctas);
-  if (warps_per_task == 8)
+  if (warps_per_task == 16)
+    jacobi_sweep_kernel<16><<<grid, 512, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
+                                                d_progress, progress_stride, d_counter, d_fault, d_active);
+  else if (warps_per_task == 8)
     jacobi_sweep_kernel<8><<<grid, 256, 0, s>>>(d_probs, batch, max_pairs, nsteps, base, tol2, dead2, d_fro2, d_dirty, d_done,
                                                d_progress, progress_stride, d_counter, d_fault, d_active);
   else
