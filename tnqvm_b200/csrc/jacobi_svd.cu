@@ -27,6 +27,14 @@ __device__ unsigned long long g_phase_cycles[8];   // developer timing (g_dbg_mo
 __device__ unsigned long long g_dmma_flops = 0;   // real flops executed on the DMMA pipe by the pair tasks (reporting only)
 __device__ int g_dbg_mode = 0;   // developer switches: 4 = rotate the pairs inside a block at every step (A/B run); 10 = per-phase clock64 timing
 
+// barriers over the first 64 threads of the CTA (warps 0-1), named barrier 1: the rotation phase does not stop the other warps
+__device__ __forceinline__ int bar64_or(int pred) {
+  int any;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %1, 0;\n\tbar.red.or.pred p, 1, 64, q;\n\tselp.s32 %0, 1, 0, p;\n\t}" : "=r"(any) : "r"(pred) : "memory");
+  return any;
+}
+__device__ __forceinline__ void bar64_sync() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {   // conj(a) * b
   return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
@@ -257,6 +265,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
   // inside each block, which every later step of the sweep leaves alone.  Lanes 0-7 of warp 0 compute the rotations
   // (two rsqrt, no division or sqrt) and their scaled form for phase C, warps 0-1 apply them to W two-sidedly.
   {
+    if (warp < 2)
     for (int r = 0; r < nrounds; ++r) {
       int rot = 0;
       if (tid < 8) {
@@ -295,7 +304,7 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
         s_rc[tid] = c; s_rs[tid] = sg; s_rp[tid] = p; s_rq[tid] = q;
         s_tp[r * 8 + tid] = tp; s_tq[r * 8 + tid] = tq;
       }
-      if (!__syncthreads_or(rot)) continue;
+      if (!bar64_or(rot)) continue;   // named barrier over warps 0-1 only (the other warps wait once, below)
       if (warp < 2) {
         // W <- J^H W J   (J_a = [[c, s],[-conj(s), c]] on columns (p,q) of pair a); one 2x2 block pair per thread
         const int ia = tid >> 3, ib = tid & 7;
@@ -313,9 +322,10 @@ __device__ __forceinline__ void pair_task(const JacobiProblem& P, int mat, int b
         sW[qa * WLD + pb] = csub(rmul(cb, t10), cmulc(sb, t11));
         sW[qa * WLD + qb] = cadd(cmul(sb, t10), rmul(cb, t11));
       }
-      __syncthreads();
+      bar64_sync();
     }
   }
+  __syncthreads();   // rotation parameters and the rotated W are complete
   if (tid == 0) {   // this task is the only owner of both blocks during this step
     if (within) { verA = __ldcg(P.ver + blkA); if (blkB >= 0) verB = __ldcg(P.ver + blkB); }
     P.ver[blkA] = verA + 1;
