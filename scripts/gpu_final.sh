@@ -1,13 +1,11 @@
 #!/bin/bash
-# End-of-round validation on one B200: full gpu test suite, bench (+ reference arm, chi=512 line), ncu launch list of one
-# bench step, full-shape configs 3 and 5.  usage (here): gpurun --timeout 900 -- 'bash scripts/gpu_final.sh rNN'
-TAG=${1:-r03z}
-OUT=gpurun_out/$TAG
-bash scripts/gpu_round.sh $TAG 2>&1 | tail -12
-BARGS="--prep random --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-peak"
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv \
-  python bench.py $BARGS > $OUT/ncu_bench.log 2>&1
-python scripts/summarize_launches.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1; cat $OUT/launches_summary.txt
-rm -f $OUT/launches.csv.gz; gzip -9 $OUT/launches.csv
-timeout 150 python scripts/configs_fullsize.py --which c3 --out $OUT/configs.jsonl 2> $OUT/c3.err | cut -c1-500; tail -2 $OUT/c3.err
-timeout 60 python scripts/configs_fullsize.py --which c5 --chi5 256 --fuse-both-upto 0 --budget 40 --out $OUT/configs.jsonl 2> $OUT/c5.err | cut -c1-500; tail -2 $OUT/c5.err
+# what the driver does at round end, on a 2-GPU box: smoke(), bench at N=1 is covered by gpu_round.sh; here N=2 under torchrun (both arms)
+OUT=gpurun_out/${1:-final}; mkdir -p $OUT
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/smoke.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > $OUT/bench_n2.json 2> $OUT/bench_n2.err; echo "bench2 rc=$?"; tail -2 $OUT/bench_n2.err
+python - <<PY
+import json
+d=json.loads(open("$OUT/bench_n2.json").read().strip().splitlines()[-1])
+print("N=2 value", d["value"], "e2e", d["e2e"]["value"], "n_gpus", d["n_gpus"], "launches", d["gpu_launches"]); print(json.dumps(d["circuit_sharded"])[:1500])
+PY
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > $OUT/bench_ref_n2.json 2> $OUT/bench_ref_n2.err; echo "ref2 rc=$?"; cut -c1-200 $OUT/bench_ref_n2.json
