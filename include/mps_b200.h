@@ -53,6 +53,10 @@ int mps_create_sharded(int n_qubits, int max_bond, double svd_cutoff, int gauge,
                        int partition_by_cost, uint64_t seed, mps_handle_t* out);
 /* the partition formula alone (no device needed): first_site[d] for d = 0..n_devices, first_site[n_devices] = n_qubits */
 int mps_shard_partition(int n_qubits, int n_devices, int max_bond, int partition_by_cost, int* first_site);
+/* the schedule of a flush on a sharded handle for a gate list (q1 = -1: single-qubit gate), as data, for tests of the host logic
+ * (no device needed).  out receives records (device, kind: 0 LAYER / 1 SEND / 2 RECV, site, slot, n_gates, gate indices...),
+ * devices in order, the ops of a device in execution order; *used = ints needed (the call fails when cap is smaller). */
+int mps_shard_plan_debug(int n_qubits, int n_devices, const int* first_site, int count, const int* q0, const int* q1, int* out, int cap, int* used);
 /* device blocks of a handle: *n_devices, and first_site[d] for d = 0..n_devices (first_site[n_devices] = n_qubits; may be NULL) */
 int mps_shard_layout(mps_handle_t h, int* n_devices, int* first_site);
 int mps_destroy(mps_handle_t h);

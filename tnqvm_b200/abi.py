@@ -18,6 +18,7 @@ SYMBOLS = {
     "mps_create": ([C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)], C.c_int),
     "mps_create_sharded": ([C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)], C.c_int),
     "mps_shard_partition": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
+    "mps_shard_plan_debug": ([C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)], C.c_int),
     "mps_shard_layout": ([C.c_void_p, C.POINTER(C.c_int), C.c_void_p], C.c_int),
     "mps_destroy": ([C.c_void_p], C.c_int),
     "mps_last_error": ([C.c_void_p], C.c_char_p),

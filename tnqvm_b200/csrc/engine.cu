@@ -1354,6 +1354,64 @@ std::vector<std::pair<int, int>> shard_partition(int n, int world, int max_bond,
 
 }  // namespace
 
+namespace {
+// The schedule of a flush on a site-sharded group: the gate list (q0, q1 or -1, skip) is cut into dependency layers exactly as
+// on one device; per layer every device gets [sites coming home] [boundary sites it lends] [boundary sites it borrows] [its
+// gates as ONE batched layer] [borrowed sites handed back].  A gate runs on the owner of its LEFT site.  Every wait (RECV)
+// refers to a SEND of an earlier phase of the same layer or of an earlier layer, so the lists cannot deadlock.
+std::vector<std::vector<ShardOp>> plan_shard_ops(int ntot, const std::vector<int>& owner, int P, const std::vector<std::array<int, 3>>& gates,
+                                                 int* n_slots, int* n_exchanges) {
+  std::vector<int> level(ntot, -1);
+  std::vector<std::vector<int>> layers;
+  for (size_t i = 0; i < gates.size(); ++i) {
+    const int q0 = gates[i][0], q1 = gates[i][1];
+    if (gates[i][2]) continue;
+    int l = level[q0];
+    if (q1 >= 0) l = std::max(l, level[q1]);
+    ++l;
+    if ((int)layers.size() <= l) layers.resize(l + 1);
+    layers[l].push_back((int)i);
+    level[q0] = l;
+    if (q1 >= 0) level[q1] = l;
+  }
+  std::vector<std::vector<ShardOp>> ops(P);
+  std::vector<int> away(ntot, -1);   // site k is on its left neighbour's device; slot of its way back (-1: at home)
+  int slots = 0, exch = 0;
+  auto op = [](ShardOp::Kind k, int site, int slot) { ShardOp o; o.kind = k; o.site = site; o.slot = slot; return o; };
+  for (auto& L : layers) {
+    std::vector<std::vector<ShardOp>> back(P), send(P), recv(P), post(P);
+    std::vector<ShardOp> run(P);
+    for (int d = 0; d < P; ++d) run[d].kind = ShardOp::LAYER;
+    for (int gi : L) {
+      const int q0 = gates[gi][0], q1 = gates[gi][1];
+      const int lo = q1 < 0 ? q0 : std::min(q0, q1), hi = q1 < 0 ? q0 : std::max(q0, q1);
+      const int A = owner[lo], B = owner[hi];
+      for (int k : {lo, hi})
+        if (away[k] >= 0) { back[owner[k]].push_back(op(ShardOp::RECV, k, away[k])); away[k] = -1; }
+      if (A != B) {
+        const int s1 = slots++, s2 = slots++;
+        send[B].push_back(op(ShardOp::SEND, hi, s1));
+        recv[A].push_back(op(ShardOp::RECV, hi, s1));
+        post[A].push_back(op(ShardOp::SEND, hi, s2));
+        away[hi] = s2;
+        ++exch;
+      }
+      run[A].gates.push_back(gi);
+    }
+    for (int d = 0; d < P; ++d) {
+      for (auto* v : {&back[d], &send[d], &recv[d]}) ops[d].insert(ops[d].end(), v->begin(), v->end());
+      if (!run[d].gates.empty()) ops[d].push_back(run[d]);
+      ops[d].insert(ops[d].end(), post[d].begin(), post[d].end());
+    }
+  }
+  for (int k = 0; k < ntot; ++k)
+    if (away[k] >= 0) ops[owner[k]].push_back(op(ShardOp::RECV, k, away[k]));   // every site is home when the flush returns
+  *n_slots = slots;
+  *n_exchanges = exch;
+  return ops;
+}
+}  // namespace
+
 // Executes the coordinator's queue on the group.  The queue is cut into dependency layers exactly as on one device; a device
 // runs, per layer, the gates whose LEFT site it owns as one batched run_layer.  For a gate on a block boundary the right
 // owner publishes its boundary site before that layer (SEND), the left owner copies it over NVLink (RECV: one
@@ -1374,53 +1432,14 @@ void mps_b200_handle::group_flush() {
     }
   if (queue.empty()) return;
   ++state_ver;
-  std::vector<int> level(ntot, -1);
-  std::vector<std::vector<int>> layers;
-  for (size_t i = 0; i < queue.size(); ++i) {
-    const QGate& g = queue[i];
-    if (g.skip) continue;
-    int l = level[g.q0];
-    if (g.q1 >= 0) l = std::max(l, level[g.q1]);
-    ++l;
-    if ((int)layers.size() <= l) layers.resize(l + 1);
-    layers[l].push_back((int)i);
-    level[g.q0] = l;
-    if (g.q1 >= 0) level[g.q1] = l;
-  }
-  // per-device op lists
-  std::vector<std::vector<ShardOp>> ops(P);
-  std::vector<int> away(ntot, -1);   // site k is on its left neighbour's device; slot of its way back (-1: at home)
+  // per-device op lists (pure host logic: plan_shard_ops, also reachable without a device through mps_shard_plan_debug)
+  std::vector<std::array<int, 3>> gl(queue.size());
+  for (size_t i = 0; i < queue.size(); ++i) gl[i] = {queue[i].q0, queue[i].q1, queue[i].skip};
+  int nslots = 0, nexch = 0;
+  std::vector<std::vector<ShardOp>> ops = plan_shard_ops(ntot, G.owner, P, gl, &nslots, &nexch);
   G.slots.clear();
-  auto new_slot = [&]() { G.slots.emplace_back(); return (int)G.slots.size() - 1; };
-  auto op = [](ShardOp::Kind k, int site, int slot) { ShardOp o; o.kind = k; o.site = site; o.slot = slot; return o; };
-  for (auto& L : layers) {
-    std::vector<std::vector<ShardOp>> back(P), send(P), recv(P), post(P);
-    std::vector<ShardOp> run(P);
-    for (int d = 0; d < P; ++d) run[d].kind = ShardOp::LAYER;
-    for (int gi : L) {
-      const QGate& g = queue[gi];
-      const int lo = g.q1 < 0 ? g.q0 : std::min(g.q0, g.q1), hi = g.q1 < 0 ? g.q0 : std::max(g.q0, g.q1);
-      const int A = G.owner[lo], B = G.owner[hi];
-      for (int k : {lo, hi})
-        if (away[k] >= 0) { back[G.owner[k]].push_back(op(ShardOp::RECV, k, away[k])); away[k] = -1; }
-      if (A != B) {
-        const int s1 = new_slot(), s2 = new_slot();
-        send[B].push_back(op(ShardOp::SEND, hi, s1));
-        recv[A].push_back(op(ShardOp::RECV, hi, s1));
-        post[A].push_back(op(ShardOp::SEND, hi, s2));
-        away[hi] = s2;
-        G.exchanges += 1;
-      }
-      run[A].gates.push_back(gi);
-    }
-    for (int d = 0; d < P; ++d) {
-      for (auto* v : {&back[d], &send[d], &recv[d]}) ops[d].insert(ops[d].end(), v->begin(), v->end());
-      if (!run[d].gates.empty()) ops[d].push_back(run[d]);
-      ops[d].insert(ops[d].end(), post[d].begin(), post[d].end());
-    }
-  }
-  for (int k = 0; k < ntot; ++k)
-    if (away[k] >= 0) ops[G.owner[k]].push_back(op(ShardOp::RECV, k, away[k]));   // every site is home when the flush returns
+  for (int i = 0; i < nslots; ++i) G.slots.emplace_back();
+  G.exchanges += nexch;
 
   G.abort = false;
   G.first_error.clear();
@@ -1951,6 +1970,30 @@ int mps_shard_partition(int n_qubits, int n_devices, int max_bond, int partition
     for (int d = 0; d < n_devices; ++d) first_site[d] = b[d].first;
     first_site[n_devices] = n_qubits;
     return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return 2;
+  }
+}
+
+int mps_shard_plan_debug(int n_qubits, int n_devices, const int* first_site, int count, const int* q0, const int* q1, int* out, int cap, int* used) {
+  try {
+    std::vector<int> owner(n_qubits, 0);
+    for (int d = 0; d < n_devices; ++d)
+      for (int k = first_site[d]; k < first_site[d + 1]; ++k) owner[k] = d;
+    std::vector<std::array<int, 3>> gl(count);
+    for (int i = 0; i < count; ++i) gl[i] = {q0[i], q1[i], 0};
+    int ns = 0, ne = 0;
+    const auto ops = plan_shard_ops(n_qubits, owner, n_devices, gl, &ns, &ne);
+    int n = 0;
+    auto put = [&](int v) { if (n < cap) out[n] = v; ++n; };
+    for (int d = 0; d < n_devices; ++d)
+      for (const ShardOp& o : ops[d]) {   // record: device, kind (0 LAYER, 1 SEND, 2 RECV), site, slot, number of gates, gate indices
+        put(d); put((int)o.kind); put(o.site); put(o.slot); put((int)o.gates.size());
+        for (int g : o.gates) put(g);
+      }
+    *used = n;
+    return n <= cap ? 0 : 2;
   } catch (const std::exception& e) {
     g_create_error = e.what();
     return 2;
