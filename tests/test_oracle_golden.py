@@ -124,3 +124,26 @@ def test_golden_fixtures():
         for bits, (re, im) in gold["amplitudes"]:
             assert abs(o.amplitude(bits) - complex(re, im)) < 1e-12, f
         assert abs(o.norm() - gold["norm"]) < 1e-12
+
+
+def test_oracle_null_rule_option_is_harmless_on_exact_runs_and_only_removes_noise_slices():
+    """OracleMPS(null_tol=...) mirrors the engine's documented deviation (numerically-null singular values count as exact zeros,
+    DESIGN.md section 1).  It is NOT part of the reference; this pins what it does: on exact (untruncated) runs the state is the
+    reference's to 1e-12 and only weightless bond slices disappear; on a truncated run of a rank-deficient circuit (GHZ prefix)
+    it never keeps more than the reference's rule does."""
+    n = 10
+    c = Cc.brickwork(n, 6, seed=4, prefix_ghz=True)
+    a = run_oracle(n, c)
+    b = O.OracleMPS(n, null_tol=1e-13).run(c)
+    assert np.abs(a.statevector() - b.statevector()).max() < 1e-12
+    assert (np.asarray(b.bond_dims()) <= np.asarray(a.bond_dims())).all() and (np.asarray(b.bond_dims()) < np.asarray(a.bond_dims())).any()
+    for k in range(n - 1):
+        sa, sb = a.singular_values(k), b.singular_values(k)
+        m = min(len(sa), len(sb))
+        # what was dropped carried no weight; the 1e-9-level differences are the reference rule's own amplified noise (sqrt of a
+        # 1e-17 singular value lands on the neighbouring sites, DESIGN.md section 1)
+        assert np.abs(sa[:m] - sb[:m]).max() < 2e-8 * sa[0] and (sa[m:] < 1e-8 * sa[0]).all()
+    at = O.OracleMPS(n, max_bond=8).run(c)
+    bt = O.OracleMPS(n, max_bond=8, null_tol=1e-13).run(c)
+    assert (np.asarray(bt.bond_dims()) <= np.asarray(at.bond_dims())).all()
+    assert 0.0 <= bt.fidelity_estimate() <= 1.0 and 0.0 <= at.fidelity_estimate() <= 1.0
