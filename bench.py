@@ -339,14 +339,20 @@ def run_b200(args):
             eng._ck(eng.L.mps_get_site(eng.h, k, hin[k].data_ptr(), shp.ctypes.data))
         zbuf = np.zeros(n)
 
+        import ctypes as C
+        ks = (C.c_int * n)(*range(n))
+        dls = (C.c_int * n)(*[s_[0] for s_ in shapes])
+        drs = (C.c_int * n)(*[s_[2] for s_ in shapes])
+        pin = (C.c_void_p * n)(*[t.data_ptr() for t in hin])
+        pout = (C.c_void_p * n)(*[t.data_ptr() for t in hout])
+
         def e2e_step(i):
-            for k in range(n):
-                eng._ck(eng.L.mps_set_site(eng.h, k, hin[k].data_ptr(), shapes[k][0], shapes[k][2]))
+            # the whole host-resident state up (one call), the gates, the observables, the whole state down (one call)
+            eng._ck(eng.L.mps_set_sites(eng.h, n, ks, pin, dls, drs))
             eng.run(compiled[i])
             z = eng.expval_z_all()
             nr = eng.norm()
-            for k in range(n):
-                eng._ck(eng.L.mps_get_site(eng.h, k, hout[k].data_ptr(), shp.ctypes.data))
+            eng._ck(eng.L.mps_get_sites(eng.h, n, ks, pout))
             return z, nr
 
         e2e_step(0)

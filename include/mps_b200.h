@@ -129,6 +129,10 @@ int mps_discarded_weight(mps_handle_t h, double* out); /* sum over truncations o
 int mps_fidelity_estimate(mps_handle_t h, double* out);
 int mps_get_site(mps_handle_t h, int k, double* out, int shape[3]);                    /* out may be NULL (shape only) */
 int mps_set_site(mps_handle_t h, int k, const double* in, int dl, int dr);
+/* the same for a list of sites with ONE wait at the end (upload / download of a host-resident state: 2 calls instead of 2 n);
+ * out[i] must hold the 2 * dl * dr complex numbers of site k[i] (shapes from mps_get_site with out = NULL, or mps_bond_dims) */
+int mps_set_sites(mps_handle_t h, int count, const int* k, const double* const* in, const int* dl, const int* dr);
+int mps_get_sites(mps_handle_t h, int count, const int* k, double* const* out);
 
 /* site-sharded multi-GPU support (replaces replicateTensorSync at ExaTnMpsVisitor.cpp:2088-2158):
  * device pointer of a site tensor for NCCL send/recv, and adoption of a received tensor */

@@ -720,3 +720,27 @@ def test_site_sharded_handle_matches_single_engine(O, devices, partition_by):
     b.reset()
     assert abs(b.norm() - 1.0) < 1e-14 and (b.bond_dims() == 1).all()
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("devices", [None, [0, 0]])
+def test_batched_site_transfer_equals_per_site_calls(devices):
+    """mps_set_sites / mps_get_sites (a host-resident state up or down in one call, one wait) against the per-site entry points,
+    on a plain and on a sharded handle."""
+    n, chi = 9, 8
+    rng = np.random.default_rng(2)
+    dims = [1] + [min(chi, 2 ** min(k + 1, n - 1 - k)) for k in range(n - 1)] + [1]
+    T = {k: rng.standard_normal((dims[k], 2, dims[k + 1])) + 1j * rng.standard_normal((dims[k], 2, dims[k + 1])) for k in range(n)}
+    a = tnqvm_b200.B200MPS(n, max_bond=chi, devices=devices)
+    b = tnqvm_b200.B200MPS(n, max_bond=chi)
+    a.set_sites(T)
+    for k in range(n):
+        b.set_site(k, T[k])
+    got = a.get_sites(range(n))
+    for k in range(n):
+        assert np.array_equal(got[k], T[k]) and np.array_equal(b.get_site(k), T[k])
+    assert abs(a.norm() - b.norm()) < 1e-12 * abs(b.norm())
+    a.run(Cc.brickwork(n, 3, seed=1)); b.run(Cc.brickwork(n, 3, seed=1))
+    for x, y in zip(a.get_sites([0, 4, n - 1]), [b.get_site(0), b.get_site(4), b.get_site(n - 1)]):
+        assert x.shape == y.shape
+    assert np.abs(a.expval_z_all() - b.expval_z_all()).max() < 1e-12 * max(1.0, abs(b.norm()))
+    a.close(); b.close()

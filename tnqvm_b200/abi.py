@@ -49,6 +49,8 @@ SYMBOLS = {
     "mps_fidelity_estimate": ([C.c_void_p, C.POINTER(C.c_double)], C.c_int),
     "mps_get_site": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
     "mps_set_site": ([C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int], C.c_int),
+    "mps_set_sites": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "mps_get_sites": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
     "mps_site_device_ptr": ([C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p], C.c_int),
     "mps_resize_site": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
     "mps_stats": ([C.c_void_p, C.c_void_p, C.c_int], C.c_int),

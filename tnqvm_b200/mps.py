@@ -248,6 +248,31 @@ class B200MPS:
         assert t.ndim == 3 and t.shape[1] == 2
         self._ck(self.L.mps_set_site(self.h, k, t.ctypes.data, t.shape[0], t.shape[2]))
 
+    def set_sites(self, tensors):
+        """{site index: (dl, 2, dr) array}: all uploads in one call, one wait (mps_set_sites)."""
+        ks = sorted(tensors)
+        arrs = [np.asfortranarray(tensors[k], dtype=np.complex128) for k in ks]
+        n = len(ks)
+        kk = (C.c_int * n)(*ks)
+        dl = (C.c_int * n)(*[a.shape[0] for a in arrs])
+        dr = (C.c_int * n)(*[a.shape[2] for a in arrs])
+        pp = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        self._ck(self.L.mps_set_sites(self.h, n, kk, pp, dl, dr))
+
+    def get_sites(self, ks):
+        """[site indices] -> list of (dl, 2, dr) arrays: all downloads in one call, one wait (mps_get_sites)."""
+        ks = list(ks)
+        shp = np.zeros(3, dtype=np.int32)
+        outs = []
+        for k in ks:
+            self._ck(self.L.mps_get_site(self.h, k, None, shp.ctypes.data))
+            outs.append(np.zeros(tuple(int(x) for x in shp), dtype=np.complex128, order="F"))
+        n = len(ks)
+        kk = (C.c_int * n)(*ks)
+        pp = (C.c_void_p * n)(*[a.ctypes.data for a in outs])
+        self._ck(self.L.mps_get_sites(self.h, n, kk, pp))
+        return outs
+
     def site_device_ptr(self, k):
         shp = np.zeros(3, dtype=np.int32)
         p = C.c_void_p()
