@@ -701,7 +701,10 @@ def test_site_sharded_handle_matches_single_engine(O, devices, partition_by):
     assert np.abs(a.expval_zz_pairs(pairs) - b.expval_zz_pairs(pairs)).max() < 1e-12   # environments hop across the block boundaries
     assert abs(a.expval_z([1, lay[1], n - 1]) - b.expval_z([1, lay[1], n - 1])) < 1e-12
     bits = [k % 2 for k in range(n)]
-    assert abs(a.amplitude(bits) - b.amplitude(bits)) < 1e-12
+    assert abs(a.amplitude(bits) - b.amplitude(bits)) < 1e-12   # the running vector hops across the block boundaries
+    open_bits = list(bits); open_bits[1] = open_bits[lay[1]] = open_bits[n - 1] = -1
+    assert np.abs(a.amplitude(open_bits) - b.amplitude(open_bits)).max() < 1e-12
+    assert np.abs(a.statevector() - b.statevector()).max() < 1e-12
     for k in (0, lay[1] - 1, lay[1], n - 2):
         assert np.abs(a.singular_values(k) - b.singular_values(k)).max() < 1e-12
     assert abs(a.discarded_weight() - b.discarded_weight()) < 1e-12

@@ -1665,6 +1665,56 @@ cplx group_sweep_weights(mps_b200_handle* h, const std::vector<std::array<double
   return out;
 }
 
+// <bits|psi> with open legs on a group: the running (rows x bond) matrix hops from device to device at the block boundaries
+// (computeWaveFuncSlice, ExaTnMpsVisitor.cpp:2588-2675; no site leaves its device)
+void group_amplitude(mps_b200_handle* h, const int8_t* bits, std::vector<cplx>& out) {
+  ShardGroup& grp = *h->grp;
+  h->flush();
+  const int P = (int)grp.sub.size(), n = h->nq;
+  int nopen = 0;
+  for (int k = 0; k < n; ++k) if (bits[k] < 0) ++nopen;
+  if (nopen > 30) throw std::runtime_error("too many open legs");
+  size_t maxd = 1;
+  for (int k = 0; k < n; ++k) maxd = std::max(maxd, (size_t)grp.sub[grp.owner[k]]->sites[k].dr);
+  const size_t elems = ((size_t)1 << nopen) * maxd * 2;
+  const cplx one(1, 0);
+  const double2* prev = nullptr;
+  size_t rows = 1;
+  for (int d = 0; d < P; ++d) {
+    mps_b200_handle* S = grp.sub[d];
+    const int k0 = grp.bounds[d].first, k1 = grp.bounds[d].second;
+    CK(cudaSetDevice(S->device));
+    S->ws.reset();
+    const size_t o0 = S->ws.reserve(elems * 16), o1 = S->ws.reserve(elems * 16);
+    S->ensure_ws(S->ws.off);
+    double2* B[2] = {(double2*)(S->ws.base + o0), (double2*)(S->ws.base + o1)};
+    if (d == 0) CK(cudaMemcpyAsync(B[0], &one, 16, cudaMemcpyHostToDevice, S->stream));
+    else group_peer_copy(S, S->stream, B[0], grp.sub[d - 1], grp.sub[d - 1]->stream, prev, rows * (size_t)grp.sub[d - 1]->sites[k0 - 1].dr);
+    int cur = 0;
+    for (int k = k0; k < k1; ++k) {
+      const SiteBuf& sb = S->sites[k];
+      GemmProblem g;
+      memset(&g, 0, sizeof(g));
+      g.A = B[cur]; g.lda = (int)rows; g.B = sb.d; g.ldb = sb.dl; g.C = B[cur ^ 1]; g.ldc = (int)rows;
+      g.M = (int)rows; g.K = sb.dl; g.alpha = 1.0;
+      if (bits[k] < 0) { g.N = 2 * sb.dr; g.b_col_stride = 1; g.b_col_off = 0; }
+      else { g.N = sb.dr; g.b_col_stride = 2; g.b_col_off = bits[k]; }
+      launch_gemm1(g, 0, S->stream);
+      S->nlaunch += 1;
+      if (bits[k] < 0) rows *= 2;
+      cur ^= 1;
+    }
+    prev = B[cur];
+    if (d == P - 1) {
+      out.resize(rows);
+      CK(cudaMemcpyAsync(out.data(), B[cur], 16 * rows, cudaMemcpyDeviceToHost, S->stream));
+      CK(cudaStreamSynchronize(S->stream));
+      CK(cudaGetLastError());
+    }
+  }
+  CK(cudaSetDevice(h->device));
+}
+
 void group_expval_z_all(mps_b200_handle* h, double* out) {
   ShardGroup& grp = *h->grp;
   GroupEnvs G;
@@ -2150,22 +2200,22 @@ int mps_expval_zz_pairs(mps_handle_t h, int reg, int npairs, const int* qi, cons
 }
 int mps_amplitude(mps_handle_t h, int reg, const int8_t* bits, double* out, size_t* len) {
   API_BEGIN(h)
-  mps_b200_handle* e = h->grp ? group_gather(h) : h;   // site-sharded group: evaluated by the engine of device 0
-  if (reg < 0 || reg >= e->nreg) throw std::runtime_error("bad register");
+  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
   std::vector<cplx> v;
-  e->amplitude(reg, bits, v);
+  if (h->grp) group_amplitude(h, bits, v);
+  else h->amplitude(reg, bits, v);
   if (out) memcpy(out, v.data(), 16 * v.size());
   if (len) *len = v.size();
   API_END(h)
 }
 int mps_statevector(mps_handle_t h, int reg, double* out) {
   API_BEGIN(h)
-  mps_b200_handle* e = h->grp ? group_gather(h) : h;   // site-sharded group: evaluated by the engine of device 0
-  if (reg < 0 || reg >= e->nreg) throw std::runtime_error("bad register");
-  if (e->nq > 30) throw std::runtime_error("state vector limited to 30 qubits");
-  std::vector<int8_t> bits(e->nq, -1);
+  if (reg < 0 || reg >= h->nreg) throw std::runtime_error("bad register");
+  if (h->nq > 30) throw std::runtime_error("state vector limited to 30 qubits");
+  std::vector<int8_t> bits(h->nq, -1);
   std::vector<cplx> v;
-  e->amplitude(reg, bits.data(), v);
+  if (h->grp) group_amplitude(h, bits.data(), v);
+  else h->amplitude(reg, bits.data(), v);
   memcpy(out, v.data(), 16 * v.size());
   API_END(h)
 }
